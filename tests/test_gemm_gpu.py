@@ -1,0 +1,150 @@
+"""GPU unit tests of the dense-layer primitives against plain PyTorch fp32 math.
+
+bf16 kernels are compared with an fp32 matmul of the SAME bf16-rounded operands, so the
+only differences are accumulation order and the final bf16 rounding of the output.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (4096, 256, 256), (8192 + 64, 256, 64),
+                                   (2048, 128, 256), (1024, 64, 256), (3 * 128 * 148 + 192, 256, 320)])
+def test_gemm_bf16_plain(cuda_dev, M, N, K):
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = _bf16(torch.randn(M, K, generator=g)).to(cuda_dev)
+    B = _bf16(torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_dev)
+    Cout = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    L.gemm_bf16(A, B, Cout, M, N, K)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (Cout.float() - ref).abs().max().item()
+    assert err < 0.03, f"max abs err {err}"
+    # bf16 rounding of an O(1) value is <= 2^-8 relative
+    assert torch.allclose(Cout.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_gemm_bf16_strided_views(cuda_dev):
+    """A and C are column slices of wider buffers (the skip-concat buffer of layer 5)."""
+    from upnerf_b200 import _lib as L
+
+    M, N, K = 1024, 256, 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    Xbuf = _bf16(torch.randn(M, 320, generator=g)).to(cuda_dev)
+    B = _bf16(torch.randn(N, K, generator=g) / 8).to(cuda_dev)
+    Cbuf = torch.zeros(M, 320, dtype=torch.bfloat16, device=cuda_dev)
+    A = Xbuf[:, 256:320]
+    L.gemm_bf16(A, B, Cbuf[:, :256], M, N, K, lda=320, ldc=320)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    assert torch.allclose(Cbuf[:, :256].float(), ref, rtol=1e-2, atol=1e-2)
+    assert (Cbuf[:, 256:] == 0).all()
+
+
+@pytest.mark.parametrize("aux_mode", [0, 1, 2])
+def test_gemm_bf16_epilogue(cuda_dev, aux_mode):
+    from upnerf_b200 import _lib as L
+
+    M, N, K, S = 64 * 37, 256, 128, 64
+    R = M // S
+    g = torch.Generator(device="cpu").manual_seed(11 + aux_mode)
+    A = _bf16(torch.randn(M, K, generator=g)).to(cuda_dev)
+    B = _bf16(torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    rbias = torch.randn(R, N, generator=g).to(cuda_dev)
+    r1row = torch.randn(M, generator=g).to(cuda_dev)
+    r1col = torch.randn(N, generator=g).to(cuda_dev)
+    aux = _bf16(torch.randn(M, N, generator=g)).to(cuda_dev)
+    hw = (torch.randn(3, N, generator=g) / N ** 0.5).to(cuda_dev)
+    hb = torch.randn(3, generator=g).to(cuda_dev)
+    hout = torch.full((M, 3), float("nan"), device=cuda_dev)
+    Cout = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    ep = L.make_epilogue(bias=bias, ray_bias=rbias, rows_per_ray=S, rank1_row=r1row, rank1_col=r1col,
+                         aux=aux if aux_mode else None, ldaux=N, aux_mode=aux_mode, act=1,
+                         head_w=hw, head_b=hb, head_act=1, head_out=hout)
+    L.gemm_bf16(A, B, Cout, M, N, K, ep=ep)
+    torch.cuda.synchronize()
+    v = A.float() @ B.float().t() + bias + rbias.repeat_interleave(S, 0) + r1row[:, None] * r1col
+    if aux_mode == 1:
+        v = v + aux.float()
+    v = torch.relu(v)
+    if aux_mode == 2:
+        v = v * (aux.float() > 0)
+    href = torch.nn.functional.softplus(v @ hw.t() + hb)
+    assert torch.allclose(Cout.float(), v, rtol=1e-2, atol=2e-2)
+    assert torch.allclose(hout, href, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (64 * 1001, 256, 320), (8192, 128, 256),
+                                   (12288, 256, 64), (64 * 77, 128, 128)])
+def test_wgrad_bf16(cuda_dev, M, N, K):
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    dY = _bf16(torch.randn(M, N, generator=g)).to(cuda_dev)
+    X = _bf16(torch.randn(M, K, generator=g)).to(cuda_dev)
+    # map packed columns [0,K-64) -> [63, ...) and the last 63 of the final 64 -> [0,63)
+    if K > 64:
+        segs = [(0, K - 64, 63), (K - 64, 63, 0)]
+        kw = K - 1
+    else:
+        segs = [(0, 63, 0)]
+        kw = 63
+    dW = torch.zeros(N, kw, device=cuda_dev)
+    db = torch.zeros(N, device=cuda_dev)
+    L.wgrad_bf16(dY, X, dW, db, M, N, K, segs)
+    torch.cuda.synchronize()
+    full = dY.float().t() @ X.float()
+    if K > 64:
+        ref = torch.cat([full[:, K - 64:K - 1], full[:, :K - 64]], 1)
+    else:
+        ref = full[:, :63]
+    scale = M ** 0.5
+    assert torch.allclose(dW / scale, ref / scale, rtol=1e-3, atol=2e-3)
+    assert torch.allclose(db / scale, dY.float().sum(0) / scale, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("trans", ["nt", "nn", "tn"])
+def test_gemm_f32_strided(cuda_dev, trans):
+    from upnerf_b200 import _lib as L
+
+    M, N, K = 333, 130, 77
+    g = torch.Generator(device="cpu").manual_seed(5)
+    if trans == "nt":   # C = A[M,K] B[N,K]^T
+        A = torch.randn(M, K, generator=g).to(cuda_dev); B = torch.randn(N, K, generator=g).to(cuda_dev)
+        sa, sb = (K, 1), (K, 1); ref = A @ B.t()
+    elif trans == "nn":  # C = A[M,K] B[K,N]
+        A = torch.randn(M, K, generator=g).to(cuda_dev); B = torch.randn(K, N, generator=g).to(cuda_dev)
+        sa, sb = (K, 1), (1, N); ref = A @ B
+    else:               # C = A[K,M]^T B[K,N]  (weight gradient form), split over k
+        A = torch.randn(K, M, generator=g).to(cuda_dev); B = torch.randn(K, N, generator=g).to(cuda_dev)
+        sa, sb = (1, M), (1, N); ref = A.t() @ B
+    Cout = torch.zeros(M, N, device=cuda_dev)
+    L.gemm_f32(A, sa, B, sb, Cout, (N, 1), M, N, K, split_k=3 if trans == "tn" else 1)
+    torch.cuda.synchronize()
+    assert torch.allclose(Cout, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_f32_epilogue(cuda_dev):
+    from upnerf_b200 import _lib as L
+
+    M, N, K, S = 256, 96, 40, 64
+    g = torch.Generator(device="cpu").manual_seed(9)
+    A = torch.randn(M, K, generator=g).to(cuda_dev)
+    B = torch.randn(N, K, generator=g).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    rbias = torch.randn(M // S, N, generator=g).to(cuda_dev)
+    aux = torch.randn(M, N, generator=g).to(cuda_dev)
+    Cout = torch.ones(M, N, device=cuda_dev)
+    ep = L.make_epilogue(bias=bias, ray_bias=rbias, rows_per_ray=S, aux=aux, ldaux=N, aux_mode=2, act=0)
+    L.gemm_f32(A, (K, 1), B, (K, 1), Cout, (N, 1), M, N, K, ep=ep, accumulate=True)
+    torch.cuda.synchronize()
+    ref = (A @ B.t() + bias + rbias.repeat_interleave(S, 0)) * (aux > 0) + 1.0
+    assert torch.allclose(Cout, ref, rtol=1e-4, atol=1e-4)

@@ -1,0 +1,82 @@
+#include "common.h"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+namespace upnerf {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so the
+// library has no link-time dependency on libcuda (this also builds on GPU-less hosts).
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  auto fn = encode_fn();
+  UPNERF_REQUIRE(fn != nullptr, UPNERF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  UPNERF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, UPNERF_ERR_BAD_SHAPE,
+                 "tensor base %p is not 16-byte aligned", base);
+  UPNERF_REQUIRE((ld * 2) % 16 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "leading dimension %llu is not a multiple of 8 elements",
+                 (unsigned long long)ld);
+  UPNERF_REQUIRE(box_cols * 2 == 128 && box_rows <= 256, UPNERF_ERR_BAD_SHAPE,
+                 "unsupported TMA box %u x %u", box_rows, box_cols);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UPNERF_REQUIRE(r == CUDA_SUCCESS, UPNERF_ERR_CUDA,
+                 "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu)",
+                 (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                 (unsigned long long)ld);
+  return UPNERF_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  return n;
+}
+
+}  // namespace upnerf
+
+extern "C" {
+
+const char* upnerf_last_error(void) { return upnerf::g_err; }
+
+int upnerf_version(void) { return 100; }
+
+int upnerf_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return 0;
+  return major == 10 ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// Dense layer on the 5th-generation tensor cores (tcgen05) -- upnerf_gemm_bf16.
+//
+//   C[M,N] (bf16) = epilogue( A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major) )
+//
+// Replaces the nn.Linear (+activation) calls of NeRF.forward (reference models/nerf.py:84-123)
+// and, with transposed weights, their data-gradient in backward.
+//
+// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
+//   warp 0      TMA producer: A tile 128x64 and B tile Nx64 per stage, 128-byte swizzle
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x N x 16)
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (thread = output row), fused
+//               bias / per-ray bias / rank-1 / aux-add / ReLU / ReLU-mask / row-dot heads,
+//               bf16 pack into a swizzled smem box, TMA store
+// Two 256-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  The aux operand (residual or ReLU mask) is TMA-loaded into the very smem
+// box the result is later stored from, two boxes ahead of its use.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "common.h"
+#include "ptx_sm100.cuh"
+
+namespace upnerf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kStages = 3;
+constexpr int kBM = 128;          // rows per tile (UMMA M)
+constexpr int kBK = 64;           // K elements per stage = one 128-byte swizzle span
+constexpr int kABytes = kBM * 128;
+constexpr int kBBytesMax = 256 * 128;
+constexpr int kCBytes = kBM * 128;  // one 128 x 64 bf16 output box
+constexpr int kNumCBuf = 4;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kMaxN = 256;
+constexpr int kMaxHeads = 3;
+
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kStages * kABytes;
+constexpr int kOffC = kOffB + kStages * kBBytesMax;
+constexpr int kOffVec = kOffC + kNumCBuf * kCBytes;
+constexpr int kVecFloats = kMaxN * (2 + kMaxHeads);
+constexpr int kOffBar = kOffVec + kVecFloats * 4;
+constexpr int kNumBars = 2 * kStages + 4 + kNumCBuf;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + slack for manual 1024-byte alignment
+
+struct GemmArgs {
+  int64_t M;
+  int N;
+  int K;
+  int num_tiles;
+  upnerf_epilogue ep;
+};
+
+__device__ __forceinline__ float softplus_ref(float x) {
+  // torch.nn.Softplus(beta=1, threshold=20)
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
+               const __grid_constant__ GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem + kOffA;
+  uint8_t* sB = smem + kOffB;
+  uint8_t* sC = smem + kOffC;
+  float* sVec = reinterpret_cast<float*>(smem + kOffVec);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + kStages;
+  uint64_t* bar_tfull = bars + 2 * kStages;
+  uint64_t* bar_tempty = bars + 2 * kStages + 2;
+  uint64_t* bar_aux = bars + 2 * kStages + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int N = args.N;
+  const int kblocks = args.K / kBK;
+  const int nchunks = N / 64;
+  const bool has_aux = args.ep.aux_mode != 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    if (has_aux) prefetch_tmap(&tmAux);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tfull[i], 1);
+      mbar_init(&bar_tempty[i], kEpiThreads);
+    }
+    for (int i = 0; i < kNumCBuf; ++i) mbar_init(&bar_aux[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  if (warp >= 2) {
+    // epilogue vectors -> smem (read with broadcast in the inner loops)
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < N; i += kEpiThreads) {
+      sVec[i] = args.ep.bias ? args.ep.bias[i] : 0.f;
+      sVec[kMaxN + i] = args.ep.rank1_row ? args.ep.rank1_col[i] : 0.f;
+      for (int h = 0; h < args.ep.n_heads; ++h)
+        sVec[(2 + h) * kMaxN + i] = args.ep.head_w[h * N + i];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = kABytes + N * 128;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], tx);
+          tma_load_2d(sA + stage * kABytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
+          tma_load_2d(sB + stage * kBBytesMax, &tmB, &bar_full[stage], kb * kBK, 0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kBM, N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        mbar_wait(&bar_tempty[acc], ((t >> 1) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
+          const uint32_t b_addr = smem_u32(sB + stage * kBBytesMax);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
+            const uint64_t db = umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128);
+            mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          mma_commit(&bar_empty[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(&bar_tfull[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    const bool leader = (threadIdx.x == 64);
+    const upnerf_epilogue& ep = args.ep;
+    const int nh = ep.n_heads;
+    int t = 0;
+    uint32_t q = 0;  // running output-box index of this CTA (selects the smem box)
+
+    // total boxes this CTA will process, for the aux prefetch
+    int my_tiles = 0;
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
+    const uint32_t total_boxes = static_cast<uint32_t>(my_tiles) * nchunks;
+    auto issue_aux = [&](uint32_t box) {
+      // box -> (tile, chunk)
+      const int lt = box / nchunks;
+      const int ch = box % nchunks;
+      const int tile = blockIdx.x + lt * gridDim.x;
+      uint64_t* b = &bar_aux[box % kNumCBuf];
+      mbar_arrive_expect_tx(b, kCBytes);
+      tma_load_2d(sC + (box % kNumCBuf) * kCBytes, &tmAux, b, ch * 64, tile * kBM);
+    };
+    if (has_aux && leader) {
+      if (total_boxes > 0) issue_aux(0);
+      if (total_boxes > 1) issue_aux(1);
+    }
+
+    for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const int64_t grow = static_cast<int64_t>(tile) * kBM + row_in_tile;
+      const bool row_ok = grow < args.M;
+      const int64_t crow = row_ok ? grow : (args.M - 1);
+      const float r1 = ep.rank1_row ? ep.rank1_row[crow] : 0.f;
+      const float* rb = ep.ray_bias ? ep.ray_bias + (crow / ep.rows_per_ray) * N : nullptr;
+      float hacc[kMaxHeads] = {0.f, 0.f, 0.f};
+
+      mbar_wait(&bar_tfull[acc], (t >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+
+      for (int ch = 0; ch < nchunks; ++ch, ++q) {
+        const uint32_t buf = q % kNumCBuf;
+        uint8_t* cbuf = sC + buf * kCBytes;
+        // The box last used this smem buffer kNumCBuf boxes ago; its TMA store must have
+        // finished reading.  The leader keeps at most one store in flight before this point.
+        if (leader) {
+          tma_store_wait_read<1>();
+          if (has_aux && q + 2 < total_boxes) issue_aux(q + 2);
+        }
+        if (has_aux) {
+          mbar_wait(&bar_aux[buf], (q / kNumCBuf) & 1);
+        } else {
+          named_bar_sync(1, kEpiThreads);
+        }
+
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(taddr + ch * 64, v0);
+        tmem_ld_32x32(taddr + ch * 64 + 32, v1);
+        tmem_ld_wait();
+        if (ch == nchunks - 1) {
+          // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before_sync();
+          mbar_arrive(&bar_tempty[acc]);
+        }
+
+        uint8_t* crow_ptr = cbuf + row_in_tile * 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int i = c8 * 8 + e;
+            v[e] = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]);
+          }
+          const int col = ch * 64 + c8 * 8;
+          const float4 b0 = *reinterpret_cast<const float4*>(&sVec[col]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&sVec[col + 4]);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          if (rb) {
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(rb + col));
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(rb + col + 4));
+            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+          }
+          if (ep.rank1_row) {
+            const float4 c0 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col]);
+            const float4 c1 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col + 4]);
+            v[0] += r1 * c0.x; v[1] += r1 * c0.y; v[2] += r1 * c0.z; v[3] += r1 * c0.w;
+            v[4] += r1 * c1.x; v[5] += r1 * c1.y; v[6] += r1 * c1.z; v[7] += r1 * c1.w;
+          }
+          uint4* slot = reinterpret_cast<uint4*>(crow_ptr + ((c8 ^ (row_in_tile & 7)) << 4));
+          float a[8];
+          if (has_aux) {
+            const uint4 au = *slot;
+            const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&au);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(ab[e]);
+              a[2 * e] = f.x;
+              a[2 * e + 1] = f.y;
+            }
+            if (ep.aux_mode == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += a[e];
+            }
+          }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (ep.aux_mode == 2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+          }
+          for (int h = 0; h < nh; ++h) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
+            hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
+                       v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+          }
+          uint4 out;
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          *slot = out;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (leader) {
+          tma_store_2d(&tmC, cbuf, ch * 64, tile * kBM);
+          tma_store_commit();
+        }
+      }
+
+      if (nh > 0 && row_ok) {
+        for (int h = 0; h < nh; ++h) {
+          float x = hacc[h] + ep.head_b[h];
+          if (ep.head_act == 1) x = softplus_ref(x);
+          else if (ep.head_act == 2) x = sigmoid_ref(x);
+          ep.head_out[grow * nh + h] = x;
+        }
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+}  // namespace upnerf
+
+extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                                int64_t ldc, int64_t M, int N, int K, const upnerf_epilogue* ep,
+                                void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(M > 0, UPNERF_ERR_BAD_SHAPE, "gemm_bf16: M=%lld", (long long)M);
+  UPNERF_REQUIRE(N >= 64 && N <= kMaxN && N % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: N=%d must be a multiple of 64 in [64,256]", N);
+  UPNERF_REQUIRE(K >= 64 && K % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: K=%d must be a positive multiple of 64", K);
+  GemmArgs args;
+  memset(&args, 0, sizeof(args));
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  const int64_t tiles = ceil_div64(M, kBM);
+  UPNERF_REQUIRE(tiles < (1ll << 30), UPNERF_ERR_BAD_SHAPE, "gemm_bf16: M too large");
+  args.num_tiles = static_cast<int>(tiles);
+  if (ep) args.ep = *ep;
+  UPNERF_REQUIRE(args.ep.n_heads >= 0 && args.ep.n_heads <= kMaxHeads, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: n_heads=%d", args.ep.n_heads);
+  UPNERF_REQUIRE(args.ep.aux_mode == 0 || args.ep.aux != nullptr, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: aux_mode set without aux");
+  UPNERF_REQUIRE(!args.ep.ray_bias || args.ep.rows_per_ray > 0, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: ray_bias without rows_per_ray");
+
+  CUtensorMap tmA, tmB, tmC, tmAux;
+  UPNERF_TRY(make_tmap_bf16_2d(&tmA, A, M, K, lda, kBM, kBK));
+  UPNERF_TRY(make_tmap_bf16_2d(&tmB, B, N, K, ldb, N, kBK));
+  UPNERF_TRY(make_tmap_bf16_2d(&tmC, C, M, N, ldc, kBM, 64));
+  if (args.ep.aux_mode != 0) {
+    UPNERF_TRY(make_tmap_bf16_2d(&tmAux, args.ep.aux, M, N, args.ep.ldaux, kBM, 64));
+  } else {
+    tmAux = tmC;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmA, tmB, tmC, tmAux, args);
+  UPNERF_CHECK_LAUNCH("gemm_tc_kernel");
+  return UPNERF_OK;
+}

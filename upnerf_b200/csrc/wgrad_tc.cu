@@ -1,0 +1,263 @@
+// Weight gradient on tcgen05 -- upnerf_wgrad_bf16.
+//
+//   dW[n, colmap(k)] += sum_m dY[m,n] * X[m,k]      db[n] += sum_m dY[m,n]
+//
+// This is the autograd backward of every nn.Linear on the path (reference
+// models/nerf.py:38-78) with respect to weight and bias.  The reduction runs over the
+// SAMPLE axis, so both operands are read "MN-major": dY[m, n] supplies A[n_out, k=m] and
+// X[m, k] supplies B[k_in, k=m] without any transpose pass -- the TMA boxes land in the
+// canonical MN-major 128-byte-swizzle layout and the UMMA descriptors say so.
+//
+// Grid: (N/128 output-row chunks) x (splits over the sample axis).  Each CTA accumulates
+// a 128 x K fp32 tile in TMEM over its sample range and adds it to dW with fp32 atomics.
+// The bias gradient is one extra N=16 MMA per K-step against an all-ones B tile.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "common.h"
+#include "ptx_sm100.cuh"
+
+namespace upnerf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kStages = 3;
+constexpr int kBS = 64;                 // samples per stage
+constexpr int kBoxBytes = kBS * 128;    // one 64-sample x 64-column bf16 box
+constexpr int kABoxes = 2;              // 128 output rows
+constexpr int kMaxBBoxes = 5;           // K <= 320
+constexpr int kStageBytes = (kABoxes + kMaxBBoxes) * kBoxBytes;
+constexpr int kOnesBytes = 1024;
+constexpr int kMaxK = 320;
+constexpr int kBiasCol = 384;           // TMEM column of the bias-gradient accumulator
+constexpr int kThreads = 192;
+
+constexpr int kOffStage = 0;
+constexpr int kOffOnes = kOffStage + kStages * kStageBytes;
+constexpr int kOffMap = kOffOnes + kOnesBytes;
+constexpr int kOffBar = kOffMap + kMaxK * 4;
+constexpr int kNumBars = 2 * kStages + 1;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;
+
+constexpr int kMaxSeg = 4;
+
+struct WgradArgs {
+  float* dW;
+  int64_t lddw;
+  float* db;
+  int64_t M;
+  int N;
+  int K;
+  int splits;
+  int64_t rows_per_split;  // multiple of kBS
+  int n_seg;
+  int seg_src[kMaxSeg], seg_len[kMaxSeg], seg_dst[kMaxSeg];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ WgradArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sStage = smem + kOffStage;
+  uint8_t* sOnes = smem + kOffOnes;
+  int* sMap = reinterpret_cast<int*>(smem + kOffMap);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + kStages;
+  uint64_t* bar_done = bars + 2 * kStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x;  // which 128 output rows
+  const int split = blockIdx.y;
+  const int K = args.K;
+  const int bboxes = K / 64;
+
+  const int64_t row_begin = static_cast<int64_t>(split) * args.rows_per_split;
+  int64_t row_end = row_begin + args.rows_per_split;
+  if (row_end > args.M) row_end = args.M;
+  const int nsteps = row_end > row_begin ? static_cast<int>((row_end - row_begin + kBS - 1) / kBS) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmX);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    // all-ones bf16 tile (B operand of the bias-gradient MMA)
+    for (int i = t; i < kOnesBytes / 4; i += 128)
+      reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    // packed column -> parameter column (or -1 for padding)
+    for (int c = t; c < kMaxK; c += 128) {
+      int d = -1;
+      for (int s = 0; s < args.n_seg; ++s)
+        if (c >= args.seg_src[s] && c < args.seg_src[s] + args.seg_len[s])
+          d = args.seg_dst[s] + (c - args.seg_src[s]);
+      sMap[c] = d;
+    }
+    fence_proxy_async_smem();  // generic-proxy writes to sOnes -> visible to the MMA
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (nsteps > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = (kABoxes + bboxes) * kBoxBytes;
+        for (int s = 0; s < nsteps; ++s) {
+          const int r0 = static_cast<int>(row_begin + static_cast<int64_t>(s) * kBS);
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&bar_full[stage], tx);
+          uint8_t* base = sStage + stage * kStageBytes;
+          for (int j = 0; j < kABoxes; ++j)
+            tma_load_2d(base + j * kBoxBytes, &tmY, &bar_full[stage], chunk * 128 + j * 64, r0);
+          for (int j = 0; j < bboxes; ++j)
+            tma_load_2d(base + (kABoxes + j) * kBoxBytes, &tmX, &bar_full[stage], j * 64, r0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const int n1 = K < 256 ? K : 256;
+        const int n2 = K - n1;
+        const uint32_t idesc1 = umma_idesc_bf16(128, n1, 1, 1);
+        const uint32_t idesc2 = umma_idesc_bf16(128, n2 > 0 ? n2 : 16, 1, 1);
+        const uint32_t idesc_ones = umma_idesc_bf16(128, 16, 1, 0);
+        const uint64_t d_ones = umma_desc(smem_u32(sOnes), 128, 256, kLayoutNone);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = 0; s < nsteps; ++s) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(sStage + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABoxes * kBoxBytes;
+#pragma unroll
+          for (int ks = 0; ks < kBS / 16; ++ks) {
+            // 16 samples = two 8-row swizzle groups (SBO = 1024); 64-column blocks are one
+            // TMA box apart (LBO = kBoxBytes).
+            const uint64_t da = umma_desc(a_addr + ks * 2048, kBoxBytes, 1024, kLayoutSw128);
+            const uint64_t db = umma_desc(b_addr + ks * 2048, kBoxBytes, 1024, kLayoutSw128);
+            const uint32_t accum = (s | ks) != 0;
+            mma_bf16_ss(tmem_base, da, db, idesc1, accum);
+            if (n2 > 0) {
+              const uint64_t db2 =
+                  umma_desc(b_addr + 4 * kBoxBytes + ks * 2048, kBoxBytes, 1024, kLayoutSw128);
+              mma_bf16_ss(tmem_base + 256, da, db2, idesc2, accum);
+            }
+            mma_bf16_ss(tmem_base + kBiasCol, da, d_ones, idesc_ones, accum);
+          }
+          mma_commit(&bar_empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        mma_commit(bar_done);
+      }
+    } else {
+      const int quad = warp & 3;
+      const int n = chunk * 128 + quad * 32 + lane;  // output row (always < N: N % 128 == 0)
+      mbar_wait(bar_done, 0);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      float* wrow = args.dW + static_cast<int64_t>(n) * args.lddw;
+      for (int g = 0; g < K / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + g * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int d = sMap[g * 32 + i];
+          if (d >= 0) atomicAdd(wrow + d, __uint_as_float(v[i]));
+        }
+      }
+      if (args.db) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + kBiasCol, v);
+        tmem_ld_wait();
+        atomicAdd(args.db + n, __uint_as_float(v[0]));
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+}  // namespace upnerf
+
+extern "C" int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx,
+                                 float* dW, int64_t lddw, float* db, int64_t M, int N, int K,
+                                 int n_seg, const int* seg_src_host, const int* seg_len_host,
+                                 const int* seg_dst_host, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(M > 0, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: M=%lld", (long long)M);
+  UPNERF_REQUIRE(N >= 128 && N <= 256 && N % 128 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "wgrad_bf16: N=%d must be 128 or 256", N);
+  UPNERF_REQUIRE(K >= 64 && K <= kMaxK && K % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "wgrad_bf16: K=%d must be a multiple of 64 in [64,320]", K);
+  UPNERF_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: n_seg=%d",
+                 n_seg);
+  WgradArgs args;
+  memset(&args, 0, sizeof(args));
+  args.dW = dW;
+  args.lddw = lddw;
+  args.db = db;
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.n_seg = n_seg;
+  for (int i = 0; i < n_seg; ++i) {
+    args.seg_src[i] = seg_src_host[i];
+    args.seg_len[i] = seg_len_host[i];
+    args.seg_dst[i] = seg_dst_host[i];
+    UPNERF_REQUIRE(seg_src_host[i] >= 0 && seg_src_host[i] + seg_len_host[i] <= K,
+                   UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: segment %d out of range", i);
+  }
+  const int chunks = N / 128;
+  int splits = sm_count() / chunks;
+  const int64_t steps = ceil_div64(M, kBS);
+  if (splits > steps) splits = static_cast<int>(steps);
+  if (splits < 1) splits = 1;
+  args.rows_per_split = ceil_div64(steps, splits) * kBS;
+  args.splits = splits;
+
+  CUtensorMap tmY, tmX;
+  UPNERF_TRY(make_tmap_bf16_2d(&tmY, dY, M, N, lddy, kBS, 64));
+  UPNERF_TRY(make_tmap_bf16_2d(&tmX, X, M, K, ldx, kBS, 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(chunks, splits);
+  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmY, tmX, args);
+  UPNERF_CHECK_LAUNCH("wgrad_tc_kernel");
+  return UPNERF_OK;
+}
