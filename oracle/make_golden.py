@@ -1,0 +1,331 @@
+"""Generate tests/golden/*.npz by running the REAL reference (mlvlab/UP-NeRF) on the CPU.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU
+box):   python -m oracle.make_golden
+
+The reference has no tests or golden vectors of its own, so these fixtures -- outputs of its
+unmodified `models/rendering.py`, `models/nerf.py`, `utils/camera.py`, `utils/ray.py`,
+`models/transient_net.py` and `losses.py` on small seeded inputs -- are what pins the oracle
+(oracle/upnerf_oracle.py) and, through it or directly, the CUDA path.  Missing third-party
+packages of the reference (easydict, kornia) are stubbed exactly as SURVEY.md Appendix A
+describes; no reference source is copied or modified.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _import_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+    def stub(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    class EasyDict(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.__dict__ = self
+
+    stub("easydict", EasyDict=EasyDict)
+
+    def create_meshgrid(H, W, normalized_coordinates=False):
+        xs, ys = torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H)
+        return torch.stack(torch.meshgrid(xs, ys, indexing="ij"), -1).permute(1, 0, 2)[None]
+
+    stub("kornia", create_meshgrid=create_meshgrid)
+    import losses as ref_losses
+    import models.nerf as ref_nerf
+    import models.rendering as ref_rendering
+    import models.transient_net as ref_tnet
+    import utils.camera as ref_camera
+    import utils.ray as ref_ray
+
+    return ref_nerf, ref_rendering, ref_camera, ref_ray, ref_tnet, ref_losses
+
+
+def _np(d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.detach().cpu().numpy()
+        else:
+            out[k] = np.asarray(v)
+    return out
+
+
+def _save(name, **arrays):
+    OUT.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / f"{name}.npz", **_np(arrays))
+    size = (OUT / f"{name}.npz").stat().st_size
+    print(f"  wrote {name}.npz ({size / 1024:.1f} KiB)")
+
+
+def _ref_nerf_module(ref_nerf, cfg, sd):
+    m = ref_nerf.NeRF(cfg.typ, D=cfg.D, W=cfg.W, skips=list(cfg.skips), encode_feat=cfg.encode_feat,
+                      feat_dim=cfg.feat_dim, xyz_L=cfg.xyz_L, dir_L=cfg.dir_L,
+                      appearance_dim=cfg.appearance_dim, candidate_dim=cfg.candidate_dim, c2f=cfg.c2f)
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m
+
+
+def _grad_digest(named_grads: dict) -> dict:
+    """Store small gradients whole; for big ones the norm plus a leading block."""
+    out = {}
+    for k, g in named_grads.items():
+        if g is None:
+            out[f"gnone__{k}"] = np.zeros(0, np.float32)
+            continue
+        g = g.detach()
+        out[f"gnorm__{k}"] = g.double().norm().float()
+        if g.numel() <= 4096:
+            out[f"gfull__{k}"] = g
+        else:
+            out[f"ghead__{k}"] = g[:4, :16].contiguous()
+    return out
+
+
+def gen_pose_rays(ref_camera, ref_ray):
+    from . import synth
+
+    n_img, R = 7, 12
+    table = synth.uniform((n_img, 6), 11, -0.4, 0.4)
+    table[0] = 0.0                         # theta = 0 row (poses start at identity)
+    table[1, :3] *= 1e-4                   # tiny rotation
+    table[2, :3] *= 6.0                    # large rotation (theta ~ 2)
+    b = synth.ray_batch(R, n_img, 5)
+    idx = b["img_idx"]
+    idx[:3] = torch.tensor([0, 1, 2])
+    table.requires_grad_(True)
+    SE3 = ref_camera.lie.se3_to_SE3(table[idx])
+    refined = ref_camera.pose.compose([SE3, b["c2w"]])
+    o, d = ref_ray.get_rays(b["directions"], refined)
+    co, cd = synth.uniform((R, 3), 21), synth.uniform((R, 3), 22)
+    ((o * co).sum() + (d * cd).sum()).backward()
+    # single-pose branch (validation path, utils/ray.py:57-65)
+    o1, d1 = ref_ray.get_rays(b["directions"], b["c2w"][0])
+    _save("pose_rays", table=table, img_idx=idx, c2w=b["c2w"], directions=b["directions"],
+          se3=SE3, refined=refined, rays_o=o, rays_d=d, co=co, cd=cd, table_grad=table.grad,
+          single_o=o1, single_d=d1)
+
+
+def gen_posenc(ref_nerf):
+    from . import synth
+    from .upnerf_oracle import NerfConfig
+
+    x = synth.uniform((10, 3), 31, -4, 4)
+    arrays = {"x": x}
+    for L in (10, 4):
+        for tag, c2f, prog in (("none", None, 0.0), ("p005", (0.1, 0.5), 0.05),
+                               ("p030", (0.1, 0.5), 0.30), ("p043", (0.1, 0.5), 0.43),
+                               ("p075", (0.1, 0.5), 0.75)):
+            cfg = NerfConfig(W=16, feat_dim=8, appearance_dim=0, candidate_dim=0, xyz_L=10, dir_L=4, c2f=c2f)
+            m = ref_nerf.NeRF("coarse", W=16, feat_dim=8, xyz_L=10, dir_L=4, appearance_dim=0,
+                              candidate_dim=0, c2f=c2f)
+            m.progress.data.fill_(prog)
+            arrays[f"L{L}_{tag}"] = m.positional_encoding(x, L)
+            arrays[f"prog_{tag}"] = torch.tensor(prog)
+    _save("posenc", **arrays)
+
+
+def gen_sample_pdf(ref_rendering):
+    from . import synth
+
+    R, nb = 9, 15
+    z = torch.sort(synth.uniform((R, nb + 1), 41, 0.1, 5.0), -1)[0]
+    bins = 0.5 * (z[:, :-1] + z[:, 1:])
+    w = synth.uniform((R, nb - 1), 42, 0, 1) ** 4
+    w[0] = 0.0                       # all-zero weights -> uniform pdf from eps
+    w[1, 3:] = 0.0                   # mass concentrated in the first bins
+    w[2, :-1] = 0.0                  # mass in the last bin
+    N = 12
+    u = synth.uniform((R, N), 43, 0, 1)
+    u[3, 0] = 0.0
+    torch.manual_seed(1234)
+    s_rand = ref_rendering.sample_pdf(bins, w, N, det=False)
+    torch.manual_seed(1234)
+    u_rand = torch.rand(R, N)
+    s_det = ref_rendering.sample_pdf(bins, w, N, det=True)
+    # explicit-u variant through the reference arithmetic (rendering.py:20-49) by patching rand
+    orig = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        s_u = ref_rendering.sample_pdf(bins, w, N, det=False)
+    finally:
+        torch.rand = orig
+    ww = w + 1e-5
+    cdf = torch.cat([torch.zeros(R, 1), torch.cumsum(ww / ww.sum(-1, keepdim=True), -1)], -1)
+    _save("sample_pdf", bins=bins, weights=w, u=u, u_rand=u_rand, samples_u=s_u, samples_rand=s_rand,
+          samples_det=s_det, cdf=cdf, inds_u=torch.searchsorted(cdf, u.contiguous(), right=True),
+          inds_det=torch.searchsorted(cdf, torch.linspace(0, 1, N).expand(R, N).contiguous(), right=True))
+
+
+NET_CASES = {
+    # name: (cfg kwargs, [(tag, sched_mult, progress)])
+    "small": (dict(W=32, feat_dim=24, appearance_dim=6, candidate_dim=4, xyz_L=10, dir_L=4, c2f=(0.1, 0.5)),
+              [("m0", 0, 0.05), ("m05", 0.5, 0.30), ("m1", 1, 0.75)]),
+    "full": (dict(W=256, feat_dim=384, appearance_dim=48, candidate_dim=16, xyz_L=10, dir_L=4, c2f=(0.1, 0.5)),
+             [("m0", 0, 0.05), ("m05", 0.5, 0.30), ("m03", 0.3, 0.22), ("m1", 1, 0.75)]),
+    "c1": (dict(W=256, encode_feat=False, feat_dim=0, appearance_dim=0, candidate_dim=0, xyz_L=10, dir_L=4, c2f=None),
+           [("m1", 1, 0.0)]),
+}
+NET_SEEDS = {"small": 3, "full": 5, "c1": 9}
+
+
+def gen_nerf_forward(ref_nerf):
+    from . import synth
+    from .upnerf_oracle import NerfConfig
+
+    M = 24
+    for name, (kw, phases) in NET_CASES.items():
+        cfg = NerfConfig(typ="coarse", **kw)
+        xyz = synth.uniform((M, 3), 51, -2.5, 2.5)
+        dirs = torch.nn.functional.normalize(synth.uniform((M, 3), 52), dim=-1)
+        a = synth.uniform((M, max(cfg.appearance_dim, 1)), 53)[:, :cfg.appearance_dim]
+        c = synth.uniform((M, max(cfg.candidate_dim, 1)), 54)[:, :cfg.candidate_dim]
+        arrays = {"xyz": xyz, "dirs": dirs, "a": a, "c": c}
+        for tag, m, prog in phases:
+            sd = synth.nerf_state(cfg, NET_SEEDS[name], progress=prog)
+            mod = _ref_nerf_module(ref_nerf, cfg, sd)
+            inputs = {"input_xyz": xyz, "input_dir": dirs}
+            if cfg.encode_appearance:
+                inputs["input_a"] = a
+            if cfg.encode_candidate:
+                inputs["input_c"] = c
+            out = mod(inputs, sched_mult=m)
+            for k, v in out.items():
+                arrays[f"{tag}__{k}"] = v
+            arrays[f"{tag}__sched_mult"] = torch.tensor(float(m))
+            arrays[f"{tag}__progress"] = torch.tensor(float(prog))
+        _save(f"nerf_forward_{name}", **arrays)
+
+
+def gen_render_rays(ref_nerf, ref_rendering):
+    from . import synth
+    from .upnerf_oracle import NerfConfig
+
+    class Emb(torch.nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.weight = torch.nn.Parameter(w.clone())
+
+        def forward(self, idx):
+            return self.weight[idx]
+
+    n_img = 5
+    for name, (kw, phases) in NET_CASES.items():
+        R, S, NI = (6, 8, 8) if name != "c1" else (6, 8, 0)
+        cfg_c, cfg_f = NerfConfig(typ="coarse", **kw), NerfConfig(typ="fine", **kw)
+        b = synth.ray_batch(R, n_img, 61)
+        from .upnerf_oracle import get_rays
+
+        o, d = get_rays(b["directions"], b["c2w"])
+        for tag, m, prog in phases:
+            for mode, perturb in (("rand", 1.0), ("det", 0.0)):
+                rays = torch.cat([o, d, b["ray_infos"]], 1).clone().requires_grad_(True)
+                sd_c = synth.nerf_state(cfg_c, NET_SEEDS[name], progress=prog)
+                sd_f = synth.nerf_state(cfg_f, NET_SEEDS[name] + 1, progress=prog)
+                models = {"nerf_coarse": _ref_nerf_module(ref_nerf, cfg_c, sd_c)}
+                if NI > 0:
+                    models["nerf_fine"] = _ref_nerf_module(ref_nerf, cfg_f, sd_f)
+                emb_w = synth.embeddings(n_img, cfg_c, 7)
+                embs = {k: Emb(v) for k, v in emb_w.items()}
+                seed = 777
+                torch.manual_seed(seed)
+                res = ref_rendering.render_rays(models=models, embeddings=embs, rays=rays, img_idx=b["img_idx"],
+                                                sched_mult=m, sched_phase=0, N_samples=S, use_disp=False,
+                                                perturb=perturb, N_importance=NI, white_back=False,
+                                                encode_feat=cfg_c.encode_feat, validation=False)
+                # replay the RNG stream in the reference's draw order
+                arrays = {"rays": rays.detach(), "img_idx": b["img_idx"], "sched_mult": torch.tensor(float(m)),
+                          "progress": torch.tensor(float(prog)), "perturb": torch.tensor(perturb),
+                          "N_samples": S, "N_importance": NI, "n_img": n_img}
+                if perturb > 0:
+                    torch.manual_seed(seed)
+                    arrays["perturb_rand"] = torch.rand(R, S)
+                    if NI > 0:
+                        if cfg_c.encode_candidate and 0 < m < 1:
+                            ns = round(m * NI)
+                            arrays["u0"] = torch.rand(R, NI - ns)
+                            arrays["u1"] = torch.rand(R, ns)
+                        else:
+                            arrays["u0"] = torch.rand(R, NI)
+                # scalar objective with fixed synthetic cotangents -> gradients
+                loss = 0.0
+                for j, (k, v) in enumerate(sorted(res.items())):
+                    cot = synth.uniform(v.shape, 900 + j, -1, 1)
+                    arrays[f"out__{k}"] = v
+                    arrays[f"cot__{k}"] = cot
+                    if "weights" in k:
+                        continue        # used detached by sample_pdf; keep them out of the objective
+                    loss = loss + (v * cot).sum()
+                loss.backward()
+                grads = {"rays": rays.grad}
+                for ek, e in embs.items():
+                    grads[f"emb_{ek}"] = e.weight.grad
+                for mk, mod in models.items():
+                    for pn, p in mod.named_parameters():
+                        grads[f"{mk}.{pn}"] = p.grad
+                arrays.update(_grad_digest(grads))
+                _save(f"render_rays_{name}_{tag}_{mode}", **arrays)
+
+
+def gen_tail(ref_tnet, ref_losses):
+    from . import synth
+
+    R, n_img = 16, 5
+    torch.manual_seed(0)
+    net = ref_tnet.TransientNet(N_images=n_img, beta_min=0.1, trasient_dim=128, feat_dim=384)
+    sd = synth.transient_state(n_img, 3)
+    assert list(sd) == list(net.state_dict())
+    net.load_state_dict(sd)
+    b = synth.ray_batch(R, n_img, 71)
+    out = net(b["feats"], b["img_idx"])
+    arrays = {"feats": b["feats"], "img_idx": b["img_idx"], "t_alpha": out["alpha"], "t_rgb": out["rgb"],
+              "t_beta": out["beta"], "rgbs": b["rgbs"]}
+    for m_tag, m in (("m0", 0), ("m05", 0.5), ("m1", 1)):
+        res = {}
+        for j, typ in enumerate(("coarse", "fine")):
+            res[f"s_depth_{typ}"] = synth.uniform((R,), 80 + j, 0.2, 4.0)
+            res[f"t_weight_{typ}"] = synth.uniform((R,), 82 + j, 0, 1)
+            res[f"feat_{typ}"] = synth.uniform((R, 384), 84 + j, -0.1, 0.1)
+            res[f"s_rgb_{typ}"] = synth.uniform((R, 3), 86 + j, 0, 1)
+        res["t_beta"], res["t_alpha"] = out["beta"], out["alpha"]
+        depth_t = synth.uniform((R,), 90, 0.2, 4.0)
+        loss = ref_losses.UPNeRFLoss(depth_mult=1e-3, alpha_reg=1.0, encode_feat=True, fine=True)
+        ld = loss(res, b["rgbs"], b["feats"], depth_t, m)
+        for k, v in res.items():
+            arrays[f"res__{k}"] = v
+        arrays["depth_t"] = depth_t
+        for k, v in ld.items():
+            arrays[f"{m_tag}__{k}"] = v
+    _save("tail", **arrays)
+
+
+def main():
+    ref_nerf, ref_rendering, ref_camera, ref_ray, ref_tnet, ref_losses = _import_reference()
+    torch.set_num_threads(4)
+    print("generating golden fixtures from", REF)
+    gen_pose_rays(ref_camera, ref_ray)
+    gen_posenc(ref_nerf)
+    gen_sample_pdf(ref_rendering)
+    gen_nerf_forward(ref_nerf)
+    gen_render_rays(ref_nerf, ref_rendering)
+    gen_tail(ref_tnet, ref_losses)
+
+
+if __name__ == "__main__":
+    main()

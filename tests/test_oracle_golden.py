@@ -1,0 +1,164 @@
+"""CPU: pin the oracle restatement against fixtures produced by the REAL reference
+(oracle/make_golden.py).  Integer results (searchsorted indices) must be bit-exact; fp32
+results are compared at 1e-5 absolute / relative (pure re-association noise)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import upnerf_oracle as O
+from oracle.make_golden import NET_CASES, NET_SEEDS
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def load(name):
+    z = np.load(GOLD / f"{name}.npz")
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def close(a, b, tol=1e-5):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.allclose(a, b, rtol=tol, atol=tol), float((a - b).abs().max())
+
+
+def test_pose_rays():
+    g = load("pose_rays")
+    table = g["table"].clone().requires_grad_(True)
+    se3 = O.se3_exp(table[g["img_idx"]])
+    close(se3, g["se3"], 1e-6)
+    refined = O.compose([se3, g["c2w"]])
+    close(refined, g["refined"], 1e-6)
+    o, d = O.get_rays(g["directions"], refined)
+    close(o, g["rays_o"], 1e-6)
+    close(d, g["rays_d"], 1e-6)
+    ((o * g["co"]).sum() + (d * g["cd"]).sum()).backward()
+    close(table.grad, g["table_grad"], 1e-5)
+    assert torch.isfinite(table.grad).all()          # theta = 0 row has finite gradients
+    o1, d1 = O.get_rays(g["directions"], g["c2w"][0])
+    close(o1, g["single_o"], 1e-6)
+    close(d1, g["single_d"], 1e-6)
+
+
+@pytest.mark.parametrize("L", [10, 4])
+def test_posenc(L):
+    g = load("posenc")
+    for tag, c2f in (("none", None), ("p005", (0.1, 0.5)), ("p030", (0.1, 0.5)), ("p043", (0.1, 0.5)),
+                     ("p075", (0.1, 0.5))):
+        got = O.positional_encoding(g["x"], L, float(g[f"prog_{tag}"]), c2f)
+        close(got, g[f"L{L}_{tag}"], 2e-6)
+
+
+def test_sample_pdf_indices_bit_exact():
+    g = load("sample_pdf")
+    cdf = O.pdf_cdf(g["weights"])
+    assert torch.equal(cdf, g["cdf"])
+    s, inds = O.sample_pdf(g["bins"], g["weights"], g["u"].shape[1], u=g["u"], return_inds=True)
+    assert torch.equal(inds, g["inds_u"])
+    assert torch.equal(s, g["samples_u"])
+    s = O.sample_pdf(g["bins"], g["weights"], g["u"].shape[1], u=g["u_rand"])
+    assert torch.equal(s, g["samples_rand"])
+    s, inds = O.sample_pdf(g["bins"], g["weights"], g["u"].shape[1], det=True, return_inds=True)
+    assert torch.equal(inds, g["inds_det"])
+    assert torch.equal(s, g["samples_det"])
+
+
+@pytest.mark.parametrize("name", list(NET_CASES))
+def test_nerf_forward(name):
+    kw, phases = NET_CASES[name]
+    g = load(f"nerf_forward_{name}")
+    cfg = O.NerfConfig(typ="coarse", **kw)
+    for tag, m, prog in phases:
+        sd = synth.nerf_state(cfg, NET_SEEDS[name], progress=prog)
+        a = g["a"] if cfg.encode_appearance else None
+        c = g["c"] if cfg.encode_candidate else None
+        out = O.nerf_forward(sd, cfg, g["xyz"], g["dirs"], a, c, m, prog)
+        keys = {k.split("__")[1] for k in g if k.startswith(tag + "__")} - {"sched_mult", "progress"}
+        assert set(out) == keys
+        for k in keys:
+            close(out[k], g[f"{tag}__{k}"], 2e-5)
+
+
+def _render_case(name, tag, mode):
+    kw, phases = NET_CASES[name]
+    g = load(f"render_rays_{name}_{tag}_{mode}")
+    m, prog = float(g["sched_mult"]), float(g["progress"])
+    m = int(m) if m in (0.0, 1.0) else m
+    cfgs = {"nerf_coarse": O.NerfConfig(typ="coarse", **kw), "nerf_fine": O.NerfConfig(typ="fine", **kw)}
+    nets = {"nerf_coarse": synth.nerf_state(cfgs["nerf_coarse"], NET_SEEDS[name], progress=prog),
+            "nerf_fine": synth.nerf_state(cfgs["nerf_fine"], NET_SEEDS[name] + 1, progress=prog)}
+    emb = synth.embeddings(int(g["n_img"]), cfgs["nerf_coarse"], 7)
+    return g, m, prog, cfgs, nets, emb
+
+
+CASES = [(n, t, md) for n, (_, ph) in NET_CASES.items() for (t, _, _) in ph for md in ("rand", "det")]
+
+
+@pytest.mark.parametrize("name,tag,mode", CASES)
+def test_render_rays_and_grads(name, tag, mode):
+    g, m, prog, cfgs, nets, emb = _render_case(name, tag, mode)
+    for sd in nets.values():
+        for k, v in sd.items():
+            if k != "progress":
+                v.requires_grad_(True)
+    for v in emb.values():
+        v.requires_grad_(True)
+    rays = g["rays"].clone().requires_grad_(True)
+    rng = O.RenderRng(perturb_rand=g.get("perturb_rand"), u=[g[k] for k in ("u0", "u1") if k in g])
+    res = O.render_rays(nets, cfgs, emb, rays, g["img_idx"], m, prog, N_samples=int(g["N_samples"]),
+                        perturb=float(g["perturb"]), N_importance=int(g["N_importance"]),
+                        encode_feat=cfgs["nerf_coarse"].encode_feat, rng=rng)
+    want = {k[5:] for k in g if k.startswith("out__")}
+    assert set(res) == want
+    loss = 0.0
+    for k in sorted(res):
+        close(res[k], g[f"out__{k}"], 3e-5)
+        if "weights" not in k:
+            loss = loss + (res[k] * g[f"cot__{k}"]).sum()
+    loss.backward()
+    grads = {"rays": rays.grad}
+    for ek, e in emb.items():
+        grads[f"emb_{ek}"] = e.grad
+    for mk, sd in nets.items():
+        if mk == "nerf_fine" and int(g["N_importance"]) == 0:
+            continue
+        for pn, p in sd.items():
+            grads[f"{mk}.{pn}"] = p.grad if pn != "progress" else None
+    checked = 0
+    for k, gr in grads.items():
+        if f"gnone__{k}" in g:
+            assert gr is None or float(gr.abs().max()) == 0.0, k
+            continue
+        ref_norm = float(g[f"gnorm__{k}"])
+        assert gr is not None, k
+        assert abs(float(gr.double().norm()) - ref_norm) <= 1e-4 * max(ref_norm, 1e-6) + 1e-7, k
+        if f"gfull__{k}" in g:
+            ref = g[f"gfull__{k}"]
+            assert float((gr - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-7, k
+        else:
+            ref = g[f"ghead__{k}"]
+            assert float((gr[:4, :16] - ref).norm()) <= 1e-4 * float(ref.norm()) + 1e-7, k
+        checked += 1
+    assert checked > 10
+
+
+def test_transient_and_loss():
+    g = load("tail")
+    res = {k[5:]: v for k, v in g.items() if k.startswith("res__")}
+    t_out = O.transient_net(synth.transient_state(5, 3), g["feats"], g["img_idx"])
+    close(t_out["alpha"], g["t_alpha"], 1e-6)
+    close(t_out["rgb"], g["t_rgb"], 1e-6)
+    close(t_out["beta"], g["t_beta"], 1e-6)
+    for tag, m in (("m0", 0), ("m05", 0.5), ("m1", 1)):
+        ld = O.upnerf_loss(res, g["rgbs"], g["feats"], g["depth_t"], m)
+        want = {k.split("__")[1] for k in g if k.startswith(tag + "__")}
+        assert set(ld) == want
+        for k in want:
+            close(ld[k], g[f"{tag}__{k}"], 1e-6)
+
+
+def test_schedule_mult():
+    assert O.schedule_mult(0.05) == 0 and O.schedule_mult(0.75) == 1
+    assert abs(O.schedule_mult(0.3) - 0.5) < 1e-12

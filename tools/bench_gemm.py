@@ -1,0 +1,60 @@
+"""Micro-benchmark of the dense-layer primitives (CUDA events, L2-exceeding inputs)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from upnerf_b200 import _lib as L
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    dev = torch.device("cuda:0")
+    M = 4096 * 192
+    for (N, K, aux) in [(256, 256, 0), (256, 256, 2), (256, 64, 0), (256, 320, 0), (128, 256, 0), (64, 256, 0)]:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        Cc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        auxt = torch.randn(M, N, device=dev).bfloat16() if aux else None
+        ep = L.make_epilogue(bias=bias, act=1, aux=auxt, ldaux=N, aux_mode=aux)
+        ms = timeit(lambda: L.gemm_bf16(A, B, Cc, M, N, K, ep=ep))
+        fl = 2.0 * M * N * K
+        by = (M * K + M * N * (2 if aux else 1)) * 2
+        print(f"gemm_bf16 M={M} N={N} K={K} aux={aux}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
+        ms = timeit(lambda: torch.matmul(A, B.t()))
+        print(f"   torch.matmul bf16: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    for (N, K) in [(256, 256), (256, 320), (128, 256), (256, 64)]:
+        dY = torch.randn(M, N, device=dev).bfloat16()
+        X = torch.randn(M, K, device=dev).bfloat16()
+        dW = torch.zeros(N, K, device=dev)
+        db = torch.zeros(N, device=dev)
+        ms = timeit(lambda: L.wgrad_bf16(dY, X, dW, db, M, N, K, [(0, K, 0)]))
+        fl = 2.0 * M * N * K
+        by = (M * K + M * N) * 2
+        print(f"wgrad_bf16 M={M} N={N} K={K}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
+        ms = timeit(lambda: torch.matmul(dY.t(), X))
+        print(f"   torch.matmul bf16: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    Mf = 256 * 192
+    A = torch.randn(Mf, 256, device=dev)
+    B = torch.randn(256, 256, device=dev)
+    Cc = torch.empty(Mf, 256, device=dev)
+    ms = timeit(lambda: L.gemm_f32(A, (256, 1), B, (256, 1), Cc, (256, 1), Mf, 256, 256))
+    print(f"gemm_f32 M={Mf}: {ms:.3f} ms {2.0 * Mf * 65536 / ms / 1e9:.2f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
