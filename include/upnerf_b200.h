@@ -91,11 +91,193 @@ int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, 
  * products):  C[m*scm + n*scn] = epi( sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] ).
  * split_k > 1 splits the k range over grid.z and accumulates with atomicAdd into C
  * (epilogue ignored, C must be pre-initialised); accumulate != 0 adds to C instead of
- * overwriting.  aux uses the strides of C. Heads are not supported here. */
+ * overwriting.  aux is row-major with row stride ldaux. Heads are not supported here. */
 int upnerf_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn,
                     int64_t sbk, float* C, int64_t scm, int64_t scn, int64_t M, int64_t N,
                     int64_t K, const upnerf_epilogue* ep, int accumulate, int split_k,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (a) Pose refinement + ray casting.
+ * Replaces, per ray: se3_refine(img_idx) -> Lie.se3_to_SE3 (utils/camera.py:87-98),
+ * Pose.compose([refine, c2w]) (utils/camera.py:43-58), get_rays (utils/ray.py:30-67) and
+ * the cat with ray_infos (models/nerf_system.py:158-166).
+ *   se3_table [n_images,6] (NULL: no refinement, plain get_rays), img_idx [R] int64,
+ *   c2w [R,3,4] or one [3,4] (c2w_is_single), directions [R,3], near_far [R,2] or NULL
+ *   -> rays [R,8] = [o, d, near, far];  pose_out [R,3,4] optional (the composed pose).
+ * Backward: d_rays [R,8] (columns 0..5 used) -> d_se3_table [n_images,6] (+=, atomics).
+ * ------------------------------------------------------------------------------------ */
+int upnerf_pose_rays_fwd(const float* se3_table, const int64_t* img_idx, const float* c2w,
+                         int c2w_is_single, const float* directions, const float* near_far,
+                         int64_t n_rays, float* rays, float* pose_out, void* stream);
+int upnerf_pose_rays_bwd(const float* se3_table, const int64_t* img_idx, const float* c2w,
+                         int c2w_is_single, const float* directions, int64_t n_rays,
+                         const float* d_rays, float* d_se3_table, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (d) Depth sampling.  models/rendering.py:231-249 (stratified), :7-50 (sample_pdf),
+ * :262-307 (resample + sort-merge).  Uniform random numbers are INPUTS (drawn by the host
+ * in the reference's order); u == NULL means det=True (linspace).
+ * ------------------------------------------------------------------------------------ */
+int upnerf_stratified_z(const float* rays, const float* perturb_rand, float perturb, int use_disp,
+                        int64_t n_rays, int n_samples, float* z, void* stream);
+/* bins [R, n_weights+1] (row stride ld_bins), weights [R, n_weights] (row stride ld_weights),
+ * u [R,N] or NULL -> samples [R,N]; optional inds [R,N] int64 (searchsorted right=True
+ * result) and cdf_out [R, n_weights+1]. */
+int upnerf_sample_pdf(const float* bins, int64_t ld_bins, const float* weights, int64_t ld_weights,
+                      const float* u, int64_t n_rays, int n_weights, int n_importance, float eps,
+                      float* samples, int64_t* inds, float* cdf_out, void* stream);
+/* torch.searchsorted(cdf, u, right=True) for row-wise sorted cdf [R,n_cdf], u [R,n_u]. */
+int upnerf_searchsorted_right(const float* cdf, int n_cdf, const float* u, int n_u, int64_t n_rays,
+                              int64_t* inds, void* stream);
+/* z [R,S] sorted coarse depths; w0/w1: coarse weights ALREADY offset to column 1 (the
+ * [:,1:-1] slice of models/rendering.py:271), row stride ld_w; draws n0 from w0 and n1 from
+ * w1 (w1 NULL or n1 0: single draw) and writes the sorted union z_fine [R, S+n0+n1]. */
+int upnerf_resample_merge(const float* z, const float* w0, const float* w1, int64_t ld_w,
+                          const float* u0, const float* u1, int n0, int n1, int64_t n_rays,
+                          int n_samples, float eps, float* z_fine, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (b) Positional encoding with the coarse-to-fine mask (models/nerf.py:126-147).
+ * band_w [L] are the per-band weights; upnerf_c2f_weights computes them on the device from
+ * the NeRF.progress scalar (models/nerf.py:137-142) so the host never synchronises.
+ * out rows: [x(3), per coordinate sin block (L) then cos block (L)], zero padded to `width`,
+ * element type by `dtype`.  ld_x is the row stride of x in floats (3 for packed xyz, 8 to
+ * encode the direction columns of a rays tensor in place).
+ * ------------------------------------------------------------------------------------ */
+int upnerf_c2f_weights(const float* progress_dev, float start, float end, int use_c2f, int L,
+                       float* band_w, void* stream);
+int upnerf_posenc_fwd(const float* x, int64_t ld_x, int64_t M, int L, const float* band_w, void* out,
+                      int64_t ld_out, int width, int dtype, void* stream);
+/* x = o + d*z formed in registers (models/rendering.py:251,308): rays [R,8], z [R,S]. */
+int upnerf_points_posenc_fwd(const float* rays, const float* z, int64_t n_rays, int n_samples, int L,
+                             const float* band_w, void* out, int64_t ld_out, int width, int dtype,
+                             void* stream);
+/* d_pe [R*S, ld_pe] -> d_rays[:,0:3] += sum_s dx, d_rays[:,3:6] += sum_s z dx. */
+int upnerf_points_posenc_bwd(const void* d_pe, int64_t ld_pe, const float* rays, const float* z,
+                             int64_t n_rays, int n_samples, int L, const float* band_w,
+                             float* d_rays, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) Alpha compositing, forward and backward (models/rendering.py:124-219).
+ * The 384-d feature heads are linear, so the kernel composites the hidden vectors that
+ * feed them (hf: 256-d output of xyz_encoding_final, g2: 128-d output of
+ * candidate_encoding) and the weight sums; see csrc/composite.cu.
+ * ------------------------------------------------------------------------------------ */
+typedef struct upnerf_composite_args {
+  int64_t R;
+  int S;
+  int cand;      /* candidate pass on: sched_mult < 1 and the candidate head is encoded */
+  int stat_rgb;  /* static rgb output on: sched_mult > 0 */
+  int feat_mode; /* 0 none, 1 features with static weights (no candidate head), 2 candidate pass */
+  int dtype;     /* element type of hf/g2/d_hf/d_g2pre */
+  const float* z;        /* [R,S] */
+  const float* s_sigma;  /* [R*S] post-softplus */
+  const float* c_sigma;  /* [R*S] */
+  const float* rgb;      /* [R*S,3] post-sigmoid */
+  const void* hf;        /* [R*S, ld_hf] */
+  int64_t ld_hf;
+  const void* g2;        /* [R*S, ld_g2] */
+  int64_t ld_g2;
+  /* forward outputs */
+  float* c_weights;  /* [R,S]  a T            (results["c_weights_*"]) */
+  float* s_weights;  /* [R,S]  a^s T^s        (results["s_weights_*"]), may be NULL */
+  float* c_depth;    /* [R] */
+  float* t_weight;   /* [R] */
+  float* s_depth;    /* [R] */
+  float* s_rgb;      /* [R,3] */
+  float* hf_ray;     /* [R,256] sum_i w_i hf_i */
+  float* g2_ray;     /* [R,128] sum_i a^c_i T_i g2_i */
+  float* ws_sum;     /* [R] sum_i w_i */
+  float* wc_sum;     /* [R] */
+  /* backward: upstream gradients (NULL = zero) */
+  const float* g_c_weights;
+  const float* g_s_weights;
+  const float* g_c_depth;
+  const float* g_t_weight;
+  const float* g_s_depth;
+  const float* g_s_rgb;
+  const float* g_hf_ray;
+  const float* g_g2_ray;
+  const float* g_ws_sum;
+  const float* g_wc_sum;
+  const float* w_csigma; /* [128] candidate_sigma.0.weight, folded into d_g2pre */
+  /* backward outputs */
+  float* d_ssig_pre; /* [R*S] w.r.t. the pre-softplus static sigma */
+  float* d_csig_pre; /* [R*S] */
+  float* d_rgb;      /* [R*S,3] w.r.t. post-sigmoid rgb */
+  void* d_hf;        /* [R*S, ld_dhf] */
+  int64_t ld_dhf;
+  void* d_g2pre;     /* [R*S, ld_dg2], already masked by g2 > 0 */
+  int64_t ld_dg2;
+} upnerf_composite_args;
+int upnerf_composite_fwd(const upnerf_composite_args* a, void* stream);
+int upnerf_composite_bwd(const upnerf_composite_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * The whole path: render_rays (models/rendering.py:53-314) with NeRF.forward
+ * (models/nerf.py:80-124) for both networks, forward and backward.
+ *
+ * Parameters of one NeRF are passed as ONE flat fp32 buffer in the reference's
+ * state_dict() order ("progress" first; upnerf_nerf_param_count/offsets describe it);
+ * gradients are accumulated (+=) into a buffer of the same layout.
+ * ------------------------------------------------------------------------------------ */
+typedef struct upnerf_net_config {
+  int D, W;               /* 8, 256 (only this trunk is implemented; skip at layer 5) */
+  int xyz_L, dir_L;       /* xyz_L <= 10 */
+  int encode_feat;        /* NeRF(encode_feat=...) */
+  int feat_dim;
+  int appearance_dim;     /* parameter layout */
+  int candidate_dim;
+  int encode_appearance;  /* run-time switches (tto clears encode_candidate) */
+  int encode_candidate;
+  int use_c2f;
+  float c2f_start, c2f_end;
+} upnerf_net_config;
+
+typedef struct upnerf_pass_io {
+  const float* params;  /* flat parameters */
+  const float* emb_a;   /* [n_images, appearance_dim] or NULL */
+  const float* emb_c;   /* [n_images, candidate_dim] or NULL */
+  /* forward outputs (NULL when the phase does not produce them) */
+  float* c_weights; float* s_weights; float* c_depth; float* s_depth; float* t_weight;
+  float* feat; float* s_rgb;
+  /* backward: upstream gradients (NULL = zero) */
+  const float* g_c_weights; const float* g_s_weights; const float* g_c_depth;
+  const float* g_s_depth; const float* g_t_weight; const float* g_feat; const float* g_s_rgb;
+  /* backward outputs, accumulated */
+  float* d_params; float* d_emb_a; float* d_emb_c;
+} upnerf_pass_io;
+
+typedef struct upnerf_render_args {
+  upnerf_net_config cfg;
+  int dtype;               /* upnerf_dtype */
+  int64_t n_rays;
+  int n_samples;           /* coarse samples per ray */
+  int n_importance;        /* 0: coarse only */
+  int n_importance_static; /* round(sched_mult*n_importance), computed by the host (Python round) */
+  int n_images;
+  float sched_mult;        /* 0: phase 0, 1: phase 2, otherwise phase 1 */
+  int use_disp;
+  float perturb;
+  const float* rays;         /* [R,8] */
+  const int64_t* img_idx;    /* [R] */
+  const float* perturb_rand; /* [R,S] when perturb > 0 */
+  const float* u0;           /* uniforms of the first sample_pdf call or NULL (det) */
+  const float* u1;           /* second call (phase 1) */
+  upnerf_pass_io coarse, fine;
+  float* z_coarse;           /* optional output [R,S] */
+  float* z_fine;             /* optional output [R,S+n_importance] */
+  float* d_rays;             /* backward output [R,8], accumulated, or NULL */
+  void* workspace;           /* activations saved by forward for backward + scratch */
+  uint64_t workspace_bytes;
+} upnerf_render_args;
+
+int64_t upnerf_nerf_param_count(const upnerf_net_config* cfg);
+/* Bytes of workspace upnerf_render_fwd/bwd need for these sizes (0 on error). */
+uint64_t upnerf_render_workspace_bytes(const upnerf_render_args* a);
+int upnerf_render_fwd(const upnerf_render_args* a, void* stream);
+int upnerf_render_bwd(const upnerf_render_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,80 @@
+"""CPU: the C-ABI shared library builds, loads and exports every symbol include/*.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from upnerf_b200 import build
+
+    return build.build()
+
+
+def test_exports_match_header(libpath):
+    hdr = (ROOT / "include" / "upnerf_b200.h").read_text()
+    declared = set(re.findall(r"\b(upnerf_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(str(libpath))
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_header(libpath, tmp_path):
+    """ctypes mirrors must have the sizes the C compiler gives the header structs."""
+    import subprocess
+
+    from upnerf_b200 import _lib as L
+
+    src = tmp_path / "sz.cpp"
+    src.write_text('#include "upnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   "sizeof(upnerf_render_args),sizeof(upnerf_composite_args),sizeof(upnerf_net_config),"
+                   "sizeof(upnerf_pass_io),sizeof(upnerf_epilogue));}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["g++", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(t) for t in (L.RenderArgs, L.CompositeArgs, L.NetConfig, L.PassIO, L.Epilogue)]
+    assert got == want
+
+
+def test_param_count_and_errors(libpath):
+    from upnerf_b200 import _lib as L
+
+    cfg = L.NetConfig(8, 256, 10, 4, 1, 384, 48, 16, 1, 1, 1, 0.1, 0.5)
+    assert L.nerf_param_count(cfg) == 818182          # SURVEY.md 8(a6), probed on the reference
+    cfg1 = L.NetConfig(8, 256, 10, 4, 0, 0, 0, 0, 0, 0, 0, 0.0, 1.0)
+    assert L.nerf_param_count(cfg1) == 595845         # config 1 static MLP
+    bad = L.NetConfig(8, 128, 10, 4, 1, 384, 48, 16, 1, 1, 1, 0.1, 0.5)
+    with pytest.raises(L.UpnerfError):
+        L.nerf_param_count(bad)
+
+
+def test_module_state_dict_matches_reference_layout():
+    import torch
+
+    from oracle import synth
+    from oracle.upnerf_oracle import NerfConfig
+    from upnerf_b200.models.nerf import NeRF, flat_parameters
+
+    for kw in (dict(), dict(encode_feat=False, feat_dim=0, appearance_dim=0, candidate_dim=0)):
+        cfg = NerfConfig(**kw)
+        m = NeRF("coarse", encode_feat=cfg.encode_feat, feat_dim=cfg.feat_dim, xyz_L=10, dir_L=4,
+                 appearance_dim=cfg.appearance_dim, candidate_dim=cfg.candidate_dim, c2f=(0.1, 0.5))
+        want = synth.nerf_param_shapes(cfg)
+        got = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+        assert got == want
+        assert flat_parameters(m).numel() == sum(int(torch.tensor(s).prod()) if s else 1 for _, s in want)
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+
+    from upnerf_b200 import _lib as L
+    from upnerf_b200.models.rendering import render_rays
+
+    with pytest.raises(L.UpnerfError):
+        render_rays({}, {}, torch.zeros(4, 8), torch.zeros(4, dtype=torch.long), 1.0)

@@ -1,0 +1,177 @@
+"""GPU parity of the whole path -- render_rays forward + backward through the reference-facing
+Python API -- against (1) golden fixtures produced by the real reference and (2) the CPU oracle
+on larger seeded batches.  Tolerances are BASELINE.json's: outputs 1e-4 abs (fp32 mode) / 2e-2
+(bf16 mode), gradients 1e-2 relative (norm-wise)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import upnerf_oracle as O
+from oracle.make_golden import NET_CASES, NET_SEEDS
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+OUT_TOL = {"fp32": 1e-4, "bf16": 2e-2}
+GRAD_TOL = {"fp32": 2e-3, "bf16": 5e-2}
+
+
+def load(name):
+    z = np.load(GOLD / f"{name}.npz")
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def build_modules(kw, seed, prog, device, n_img, emb_seed=7, fine=True):
+    from upnerf_b200.models.nerf import NeRF
+
+    cfg_c, cfg_f = O.NerfConfig(typ="coarse", **kw), O.NerfConfig(typ="fine", **kw)
+    sds = {"nerf_coarse": synth.nerf_state(cfg_c, seed, progress=prog), "nerf_fine": synth.nerf_state(cfg_f, seed + 1, progress=prog)}
+    models = {}
+    for name, cfg in (("nerf_coarse", cfg_c), ("nerf_fine", cfg_f)):
+        if name == "nerf_fine" and not fine:
+            continue
+        m = NeRF(cfg.typ, encode_feat=cfg.encode_feat, feat_dim=cfg.feat_dim, xyz_L=cfg.xyz_L, dir_L=cfg.dir_L,
+                 appearance_dim=cfg.appearance_dim, candidate_dim=cfg.candidate_dim, c2f=cfg.c2f)
+        m.load_state_dict(sds[name])
+        models[name] = m.to(device)
+    emb_w = synth.embeddings(n_img, cfg_c, emb_seed)
+    embs = {}
+    for k, w in emb_w.items():
+        e = torch.nn.Embedding(*w.shape)
+        e.weight.data.copy_(w)
+        embs[k] = e.to(device)
+    return {"nerf_coarse": cfg_c, "nerf_fine": cfg_f}, sds, models, emb_w, embs
+
+
+CASES = [(n, t) for n, (_, ph) in NET_CASES.items() if n != "small" for (t, _, _) in ph]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["rand", "det"])
+@pytest.mark.parametrize("name,tag", CASES)
+def test_render_rays_golden(cuda_dev, name, tag, mode, precision):
+    from upnerf_b200.models.rendering import render_rays
+
+    kw, _ = NET_CASES[name]
+    g = load(f"render_rays_{name}_{tag}_{mode}")
+    m, prog = float(g["sched_mult"]), float(g["progress"])
+    m = int(m) if m in (0.0, 1.0) else m
+    NI = int(g["N_importance"])
+    cfgs, sds, models, emb_w, embs = build_modules(kw, NET_SEEDS[name], prog, cuda_dev, int(g["n_img"]), fine=NI > 0)
+    rays = g["rays"].to(cuda_dev).requires_grad_(True)
+    rng = dict(perturb_rand=g.get("perturb_rand"), u=[g[k] for k in ("u0", "u1") if k in g])
+    res = render_rays(models=models, embeddings=embs, rays=rays, img_idx=g["img_idx"].to(cuda_dev), sched_mult=m,
+                      sched_phase=0, N_samples=int(g["N_samples"]), use_disp=False, perturb=float(g["perturb"]),
+                      N_importance=NI, white_back=False, encode_feat=cfgs["nerf_coarse"].encode_feat,
+                      validation=False, rng=rng, precision=precision)
+    want = {k[5:] for k in g if k.startswith("out__")}
+    assert set(res) == want
+    tol = OUT_TOL[precision]
+    loss = 0.0
+    for k in sorted(res):
+        ref = g[f"out__{k}"]
+        got = res[k]
+        assert got.shape == ref.shape and got.dtype == torch.float32, k
+        if precision == "fp32":
+            assert float((got.detach().cpu() - ref).abs().max()) <= tol, (k, float((got.detach().cpu() - ref).abs().max()))
+        else:
+            # bf16: fine-pass tensors are compared after the resampling, which may legitimately move
+            # samples; bound the error on per-ray outputs only
+            if got.dim() == 1 or got.shape[-1] in (3,) or k.startswith("feat"):
+                err = float((got.detach().cpu() - ref).abs().max())
+                scale = max(1.0, float(ref.abs().max()))
+                assert err <= tol * scale, (k, err)
+        if "weights" not in k:
+            loss = loss + (got * g[f"cot__{k}"].to(cuda_dev)).sum()
+    loss.backward()
+    grads = {"rays": rays.grad}
+    for ek, e in embs.items():
+        grads[f"emb_{ek}"] = e.weight.grad
+    for mk, mod in models.items():
+        for pn, p in mod.named_parameters():
+            grads[f"{mk}.{pn}"] = p.grad
+    gtol = GRAD_TOL[precision]
+    checked = 0
+    for k, gr in grads.items():
+        if f"gnone__{k}" in g:
+            assert gr is None or float(gr.abs().max()) == 0.0, k
+            continue
+        if f"gnorm__{k}" not in g:
+            continue
+        ref_norm = float(g[f"gnorm__{k}"])
+        assert gr is not None, k
+        gr = gr.detach().cpu()
+        if f"gfull__{k}" in g:
+            ref = g[f"gfull__{k}"]
+            err = float((gr.reshape(ref.shape) - ref).norm())
+            assert err <= gtol * ref_norm + 1e-6, (k, err, ref_norm)
+        else:
+            assert abs(float(gr.double().norm()) - ref_norm) <= gtol * ref_norm + 1e-6, (k, float(gr.norm()), ref_norm)
+            ref = g[f"ghead__{k}"]
+            err = float((gr[:4, :16] - ref).norm())
+            assert err <= 3 * gtol * float(ref.norm()) + 1e-3 * gtol * ref_norm + 1e-7, (k, err)
+        checked += 1
+    assert checked > 10
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag,m,prog", [("m0", 0, 0.05), ("m05", 0.5, 0.30), ("m1", 1, 0.75)])
+def test_render_rays_vs_oracle_1024(cuda_dev, tag, m, prog, precision):
+    """Config-2-shaped batch (64+64 samples, all heads, embeddings) against the CPU oracle."""
+    from upnerf_b200.models.rendering import render_rays
+
+    kw, _ = NET_CASES["full"]
+    R, S, NI, n_img = 256, 64, 64, 763
+    cfgs, sds, models, emb_w, embs = build_modules(kw, 21, prog, cuda_dev, n_img, emb_seed=9)
+    b = synth.ray_batch(R, n_img, 33)
+    o, d = O.get_rays(b["directions"], b["c2w"])
+    rays0 = torch.cat([o, d, b["ray_infos"]], 1)
+    ns = round(m * NI) if 0 < m < 1 else 0
+    rng = dict(perturb_rand=synth.uniform((R, S), 41, 0, 1),
+               u=[synth.uniform((R, NI - ns), 42, 0, 1)] + ([synth.uniform((R, ns), 43, 0, 1)] if ns else []))
+    # oracle
+    for sd in sds.values():
+        for k, v in sd.items():
+            if k != "progress":
+                v.requires_grad_(True)
+    emb_o = {k: v.clone().requires_grad_(True) for k, v in emb_w.items()}
+    rays_o = rays0.clone().requires_grad_(True)
+    torch.set_num_threads(8)
+    ref = O.render_rays(sds, cfgs, emb_o, rays_o, b["img_idx"], m, prog, N_samples=S, perturb=1.0, N_importance=NI,
+                        rng=O.RenderRng(perturb_rand=rng["perturb_rand"], u=list(rng["u"])))
+    cots = {k: synth.uniform(v.shape, 500 + i) / v[0].numel() for i, (k, v) in enumerate(sorted(ref.items()))}
+    sum((ref[k] * cots[k]).sum() for k in ref if "weights" not in k).backward()
+    # CUDA path
+    rays = rays0.to(cuda_dev).requires_grad_(True)
+    res = render_rays(models=models, embeddings=embs, rays=rays, img_idx=b["img_idx"].to(cuda_dev), sched_mult=m,
+                      N_samples=S, perturb=1.0, N_importance=NI, encode_feat=True, rng=rng, precision=precision)
+    assert list(res) == list(ref)
+    tol = OUT_TOL[precision]
+    for k in ref:
+        if precision == "bf16" and "fine" in k and res[k].dim() == 2 and res[k].shape[1] == S + NI:
+            continue    # per-sample fine weights follow the (precision-dependent) resampled depths
+        err = float((res[k].detach().cpu() - ref[k].detach()).abs().max())
+        assert err <= tol * max(1.0, float(ref[k].abs().max())), (k, err)
+    sum((res[k] * cots[k].to(cuda_dev)).sum() for k in res if "weights" not in k).backward()
+    gtol = 1e-2 if precision == "fp32" else 6e-2
+
+    def rel(a, b_):
+        return float((a.detach().cpu() - b_).norm() / (b_.norm() + 1e-20))
+
+    assert rel(rays.grad[:, :6], rays_o.grad[:, :6]) < gtol
+    for ek in emb_o:
+        if emb_o[ek].grad is not None and float(emb_o[ek].grad.abs().max()) > 0:
+            assert rel(embs[ek].weight.grad, emb_o[ek].grad) < gtol, ek
+    worst = 0.0
+    for mk, mod in models.items():
+        for pn, p in mod.named_parameters():
+            gref = sds[mk][pn].grad if pn != "progress" else None
+            if gref is None or float(gref.abs().max()) == 0:
+                assert p.grad is None or float(p.grad.abs().max()) == 0, (mk, pn)
+                continue
+            r = rel(p.grad, gref)
+            worst = max(worst, r)
+            assert r < gtol, (mk, pn, r)
+    print(f"[{precision} {tag}] worst relative parameter-gradient error {worst:.2e}")

@@ -133,3 +133,155 @@ def gemm_f32(A, sa, B, sb, C_out, sc, M, N, K, ep: Epilogue | None = None, accum
                                C.byref(ep) if ep is not None else None, C.c_int(int(accumulate)),
                                C.c_int(split_k), stream_ptr())
     check(st, "upnerf_gemm_f32")
+
+
+# ---------------------------------------------------------------------------------------
+# Structs of the render-level ABI (mirror include/upnerf_b200.h field for field)
+# ---------------------------------------------------------------------------------------
+F32, BF16 = 0, 1
+
+
+class NetConfig(C.Structure):
+    _fields_ = [("D", C.c_int), ("W", C.c_int), ("xyz_L", C.c_int), ("dir_L", C.c_int),
+                ("encode_feat", C.c_int), ("feat_dim", C.c_int), ("appearance_dim", C.c_int),
+                ("candidate_dim", C.c_int), ("encode_appearance", C.c_int), ("encode_candidate", C.c_int),
+                ("use_c2f", C.c_int), ("c2f_start", C.c_float), ("c2f_end", C.c_float)]
+
+
+_PASS_PTRS = ["params", "emb_a", "emb_c",
+              "c_weights", "s_weights", "c_depth", "s_depth", "t_weight", "feat", "s_rgb",
+              "g_c_weights", "g_s_weights", "g_c_depth", "g_s_depth", "g_t_weight", "g_feat", "g_s_rgb",
+              "d_params", "d_emb_a", "d_emb_c"]
+
+
+class PassIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _PASS_PTRS]
+
+
+class RenderArgs(C.Structure):
+    _fields_ = [("cfg", NetConfig), ("dtype", C.c_int), ("n_rays", C.c_int64), ("n_samples", C.c_int),
+                ("n_importance", C.c_int), ("n_importance_static", C.c_int), ("n_images", C.c_int),
+                ("sched_mult", C.c_float), ("use_disp", C.c_int), ("perturb", C.c_float),
+                ("rays", C.c_void_p), ("img_idx", C.c_void_p), ("perturb_rand", C.c_void_p),
+                ("u0", C.c_void_p), ("u1", C.c_void_p), ("coarse", PassIO), ("fine", PassIO),
+                ("z_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("d_rays", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class CompositeArgs(C.Structure):
+    _fields_ = ([("R", C.c_int64), ("S", C.c_int), ("cand", C.c_int), ("stat_rgb", C.c_int),
+                 ("feat_mode", C.c_int), ("dtype", C.c_int)]
+                + [(n, C.c_void_p) for n in ("z", "s_sigma", "c_sigma", "rgb", "hf")]
+                + [("ld_hf", C.c_int64), ("g2", C.c_void_p), ("ld_g2", C.c_int64)]
+                + [(n, C.c_void_p) for n in ("c_weights", "s_weights", "c_depth", "t_weight", "s_depth", "s_rgb",
+                                             "hf_ray", "g2_ray", "ws_sum", "wc_sum",
+                                             "g_c_weights", "g_s_weights", "g_c_depth", "g_t_weight", "g_s_depth",
+                                             "g_s_rgb", "g_hf_ray", "g_g2_ray", "g_ws_sum", "g_wc_sum", "w_csigma",
+                                             "d_ssig_pre", "d_csig_pre", "d_rgb", "d_hf")]
+                + [("ld_dhf", C.c_int64), ("d_g2pre", C.c_void_p), ("ld_dg2", C.c_int64)])
+
+
+def _vp(t):
+    return None if t is None else t.data_ptr()
+
+
+def nerf_param_count(cfg: NetConfig) -> int:
+    f = lib().upnerf_nerf_param_count
+    f.restype = C.c_int64
+    n = f(C.byref(cfg))
+    if n < 0:
+        check(2, "upnerf_nerf_param_count")
+    return int(n)
+
+
+def render_workspace_bytes(args: RenderArgs) -> int:
+    f = lib().upnerf_render_workspace_bytes
+    f.restype = C.c_uint64
+    n = int(f(C.byref(args)))
+    if n == 0:
+        check(1, "upnerf_render_workspace_bytes")
+    return n
+
+
+def render_fwd(args: RenderArgs) -> None:
+    check(lib().upnerf_render_fwd(C.byref(args), stream_ptr()), "upnerf_render_fwd")
+
+
+def render_bwd(args: RenderArgs) -> None:
+    check(lib().upnerf_render_bwd(C.byref(args), stream_ptr()), "upnerf_render_bwd")
+
+
+def composite_fwd(args: CompositeArgs) -> None:
+    check(lib().upnerf_composite_fwd(C.byref(args), stream_ptr()), "upnerf_composite_fwd")
+
+
+def composite_bwd(args: CompositeArgs) -> None:
+    check(lib().upnerf_composite_bwd(C.byref(args), stream_ptr()), "upnerf_composite_bwd")
+
+
+def pose_rays_fwd(table, img_idx, c2w, directions, near_far, rays, pose_out=None):
+    single = 1 if c2w.dim() == 2 else 0
+    st = lib().upnerf_pose_rays_fwd(ptr(table), ptr(img_idx), ptr(c2w), C.c_int(single), ptr(directions),
+                                    ptr(near_far), _i64(directions.shape[0]), ptr(rays), ptr(pose_out),
+                                    stream_ptr())
+    check(st, "upnerf_pose_rays_fwd")
+
+
+def pose_rays_bwd(table, img_idx, c2w, directions, d_rays, d_table):
+    single = 1 if c2w.dim() == 2 else 0
+    st = lib().upnerf_pose_rays_bwd(ptr(table), ptr(img_idx), ptr(c2w), C.c_int(single), ptr(directions),
+                                    _i64(directions.shape[0]), ptr(d_rays), ptr(d_table), stream_ptr())
+    check(st, "upnerf_pose_rays_bwd")
+
+
+def stratified_z(rays, perturb_rand, perturb, use_disp, S, z):
+    st = lib().upnerf_stratified_z(ptr(rays), ptr(perturb_rand), C.c_float(perturb), C.c_int(int(use_disp)),
+                                   _i64(rays.shape[0]), C.c_int(S), ptr(z), stream_ptr())
+    check(st, "upnerf_stratified_z")
+
+
+def sample_pdf(bins, weights, u, N, eps, samples, inds=None, cdf_out=None):
+    R, nw = weights.shape
+    st = lib().upnerf_sample_pdf(ptr(bins), _i64(bins.stride(0)), ptr(weights), _i64(weights.stride(0)), ptr(u),
+                                 _i64(R), C.c_int(nw), C.c_int(N), C.c_float(eps), ptr(samples), ptr(inds),
+                                 ptr(cdf_out), stream_ptr())
+    check(st, "upnerf_sample_pdf")
+
+
+def searchsorted_right(cdf, u, inds):
+    st = lib().upnerf_searchsorted_right(ptr(cdf), C.c_int(cdf.shape[1]), ptr(u), C.c_int(u.shape[1]),
+                                         _i64(cdf.shape[0]), ptr(inds), stream_ptr())
+    check(st, "upnerf_searchsorted_right")
+
+
+def resample_merge(z, w0, w1, ld_w, u0, u1, n0, n1, eps, z_fine):
+    R, S = z.shape
+    st = lib().upnerf_resample_merge(ptr(z), ptr(w0), ptr(w1), _i64(ld_w), ptr(u0), ptr(u1), C.c_int(n0),
+                                     C.c_int(n1), _i64(R), C.c_int(S), C.c_float(eps), ptr(z_fine), stream_ptr())
+    check(st, "upnerf_resample_merge")
+
+
+def c2f_weights(progress_dev, start, end, use_c2f, L, out):
+    st = lib().upnerf_c2f_weights(ptr(progress_dev), C.c_float(start), C.c_float(end), C.c_int(int(use_c2f)),
+                                  C.c_int(L), ptr(out), stream_ptr())
+    check(st, "upnerf_c2f_weights")
+
+
+def posenc_fwd(x, ld_x, M, L, band_w, out, ld_out, width, dtype):
+    st = lib().upnerf_posenc_fwd(ptr(x), _i64(ld_x), _i64(M), C.c_int(L), ptr(band_w), ptr(out), _i64(ld_out),
+                                 C.c_int(width), C.c_int(dtype), stream_ptr())
+    check(st, "upnerf_posenc_fwd")
+
+
+def points_posenc_fwd(rays, z, L, band_w, out, ld_out, width, dtype):
+    R, S = z.shape
+    st = lib().upnerf_points_posenc_fwd(ptr(rays), ptr(z), _i64(R), C.c_int(S), C.c_int(L), ptr(band_w), ptr(out),
+                                        _i64(ld_out), C.c_int(width), C.c_int(dtype), stream_ptr())
+    check(st, "upnerf_points_posenc_fwd")
+
+
+def points_posenc_bwd(d_pe, ld_pe, rays, z, L, band_w, d_rays, dtype):
+    R, S = z.shape
+    st = lib().upnerf_points_posenc_bwd(ptr(d_pe), _i64(ld_pe), ptr(rays), ptr(z), _i64(R), C.c_int(S), C.c_int(L),
+                                        ptr(band_w), ptr(d_rays), C.c_int(dtype), stream_ptr())
+    check(st, "upnerf_points_posenc_bwd")

@@ -6,6 +6,8 @@
 // (per-ray embedding biases, the 384-d feature projection applied AFTER compositing).
 // Generic strides let the same kernel serve forward (A.W^T), data gradient (dY.W) and
 // weight gradient (dY^T.X, split over the sample axis with atomics) without transposes.
+#include <string.h>
+
 #include "common.h"
 
 namespace upnerf {
@@ -23,6 +25,7 @@ struct SimtArgs {
   int64_t M, N, K;
   int accumulate;
   int split_k;
+  int atomic;  // accumulate with atomicAdd (split-k requested), epilogue skipped
   int64_t k_per_split;
   upnerf_epilogue ep;
 };
@@ -89,7 +92,7 @@ gemm_simt_kernel(const SimtArgs a) {
       if (n >= a.N) continue;
       float v = acc[i][j];
       float* c = a.C + m * a.scm + n * a.scn;
-      if (a.split_k > 1) {
+      if (a.atomic) {
         atomicAdd(c, v);
         continue;
       }
@@ -125,6 +128,7 @@ extern "C" int upnerf_gemm_f32(const float* A, int64_t sam, int64_t sak, const f
   a.M = M; a.N = N; a.K = K;
   a.accumulate = accumulate;
   if (split_k < 1) split_k = 1;
+  a.atomic = split_k > 1;
   // k ranges are multiples of TK so tiles of different splits never overlap
   int64_t kps = ceil_div64(ceil_div64(K, split_k), TK) * TK;
   split_k = static_cast<int>(ceil_div64(K, kps));

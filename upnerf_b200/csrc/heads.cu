@@ -1,0 +1,276 @@
+// Small kernels around the dense layers: per-ray embedding gathers/scatters
+// (models/rendering.py:255-258,309-312), the rgb output layer's backward
+// (models/nerf.py:59-64), per-ray reductions of per-sample gradients, the fp32-mode
+// row-dot heads (share_sigma / candidate_sigma / rgb out, models/nerf.py:51,62,74) and
+// weight packing (fp32 master parameters -> bf16/fp32 GEMM operands, padded / permuted /
+// transposed as the kernels want them).
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "internal.h"
+
+namespace upnerf {
+namespace {
+
+__device__ __forceinline__ float ldv(const float* p) { return *p; }
+__device__ __forceinline__ float ldv(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stv(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stv(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
+                                   int64_t R, int dim, float* __restrict__ out, int64_t ld_out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= R * dim) return;
+  const int64_t r = i / dim;
+  const int c = static_cast<int>(i - r * dim);
+  out[r * ld_out + c] = table[idx[r] * dim + c];
+}
+
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, int64_t ld_src,
+                                        const int64_t* __restrict__ idx, int64_t R, int dim,
+                                        float* __restrict__ table) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= R * dim) return;
+  const int64_t r = i / dim;
+  const int c = static_cast<int>(i - r * dim);
+  atomicAdd(table + idx[r] * dim + c, src[r * ld_src + c]);
+}
+
+// out[r, :] = sum over the S samples of ray r of X[r*S + s, :]   (N = 128, one warp per ray)
+template <typename T>
+__global__ void __launch_bounds__(128)
+ray_sum128_kernel(const T* __restrict__ X, int64_t ld, int64_t R, int S, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * 4ll + warp;
+  if (r >= R) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* base = X + r * S * ld + lane * 4;
+  for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += ldv(base + s * ld + e);
+  }
+  float* o = out + r * 128 + lane * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e] = acc[e];
+}
+
+// Backward of  rgb = sigmoid(W2 q + b2)  with q = relu(...) (N = 128 hidden units):
+//   d q_pre = (W2^T (d_rgb * rgb (1-rgb))) * (q > 0);  dW2, db2 accumulated;  per-ray sum of
+//   d q_pre -> d_raybias (the per-ray bias of the hidden layer carries direction/appearance).
+template <typename T>
+__global__ void __launch_bounds__(256)
+rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restrict__ rgb,
+                    const float* __restrict__ d_rgb, const float* __restrict__ W2, int64_t R, int S,
+                    T* __restrict__ dQ, int64_t lddq, float* __restrict__ d_raybias,
+                    float* __restrict__ dW2, float* __restrict__ db2) {
+  __shared__ float red[8][3 * 128 + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float w2[3][4];
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w2[h][e] = W2[h * 128 + lane * 4 + e];
+  float aw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float ab[3] = {0.f, 0.f, 0.f};
+  for (int64_t r = blockIdx.x * 8ll + warp; r < R; r += gridDim.x * 8ll) {
+    float rb[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < S; ++s) {
+      const int64_t m = r * S + s;
+      float g[3];
+#pragma unroll
+      for (int h = 0; h < 3; ++h) {
+        const float y = rgb[m * 3 + h];
+        g[h] = d_rgb[m * 3 + h] * y * (1.f - y);
+        ab[h] += g[h];
+      }
+      const T* q = Q + m * ldq + lane * 4;
+      T* dq = dQ + m * lddq + lane * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float qv = ldv(q + e);
+        const float d = qv > 0.f ? (g[0] * w2[0][e] + g[1] * w2[1][e] + g[2] * w2[2][e]) : 0.f;
+        stv(dq + e, d);
+        rb[e] += d;
+        aw[0][e] += g[0] * qv;
+        aw[1][e] += g[1] * qv;
+        aw[2][e] += g[2] * qv;
+      }
+    }
+    float* o = d_raybias + r * 128 + lane * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = rb[e];
+  }
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[warp][h * 128 + lane * 4 + e] = aw[h][e];
+  if (lane == 0) {
+    red[warp][384] = ab[0];
+    red[warp][385] = ab[1];
+    red[warp][386] = ab[2];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 387; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][i];
+    if (i < 384) atomicAdd(dW2 + i, t); else atomicAdd(db2 + (i - 384), t);
+  }
+}
+
+// out[n] += sum_m s[m] X[m,n];  out_s += sum_m s[m]   (s == nullptr -> ones).  N <= 256, even.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowscale_colsum_kernel(const T* __restrict__ X, int64_t ld, const float* __restrict__ s, int64_t M,
+                       int N, float* __restrict__ out, float* __restrict__ out_s) {
+  __shared__ float red[256][2];
+  const int half = N / 2;
+  const int groups = 256 / half;            // rows handled concurrently by one block
+  const int g = threadIdx.x / half;
+  const int c2 = threadIdx.x % half;
+  float a0 = 0.f, a1 = 0.f, as = 0.f;
+  if (g < groups) {
+    for (int64_t m = blockIdx.x * static_cast<int64_t>(groups) + g; m < M;
+         m += static_cast<int64_t>(gridDim.x) * groups) {
+      const float sv = s ? s[m] : 1.f;
+      a0 = fmaf(sv, ldv(X + m * ld + 2 * c2), a0);
+      a1 = fmaf(sv, ldv(X + m * ld + 2 * c2 + 1), a1);
+      as += sv;
+    }
+  }
+  red[threadIdx.x][0] = a0;
+  red[threadIdx.x][1] = a1;
+  __syncthreads();
+  if (threadIdx.x < half) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int k = 0; k < groups; ++k) {
+      t0 += red[k * half + threadIdx.x][0];
+      t1 += red[k * half + threadIdx.x][1];
+    }
+    atomicAdd(out + 2 * threadIdx.x, t0);
+    atomicAdd(out + 2 * threadIdx.x + 1, t1);
+  }
+  if (out_s && c2 == 0 && g < groups) atomicAdd(out_s, as);
+}
+
+// fp32-mode row-dot heads: out[m,h] = act(X[m,:] . w[h,:] + b[h]); one warp per row.
+__global__ void __launch_bounds__(128)
+rowdot_head_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N, int nh,
+                   const float* __restrict__ w, const float* __restrict__ b, int act,
+                   float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = blockIdx.x * 4ll + warp;
+  if (m >= M) return;
+  for (int h = 0; h < nh; ++h) {
+    float acc = 0.f;
+    for (int n = lane; n < N; n += 32) acc = fmaf(X[m * ld + n], w[h * N + n], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float x = acc + b[h];
+      if (act == 1) x = softplus_ref(x);
+      else if (act == 2) x = sigmoid_ref(x);
+      out[m * nh + h] = x;
+    }
+  }
+}
+
+template <typename T>
+__global__ void pack_kernel(const PackList list) {
+  const PackOp& op = list.ops[blockIdx.y];
+  const int64_t n = static_cast<int64_t>(op.rows) * op.cols;
+  T* dst = static_cast<T*>(op.dst);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / op.cols), c = static_cast<int>(i % op.cols);
+    const float v = op.src[static_cast<int64_t>(r) * op.ld_src + c];
+    if (op.transpose) stv(dst + static_cast<int64_t>(c) * op.ld_dst + r, v);
+    else stv(dst + static_cast<int64_t>(r) * op.ld_dst + c, v);
+  }
+}
+
+}  // namespace
+
+int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, float* out, int64_t ld_out,
+                cudaStream_t st) {
+  const int64_t n = R * dim;
+  gather_rows_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(table, idx, R, dim, out, ld_out);
+  UPNERF_CHECK_LAUNCH("gather_rows_kernel");
+  return UPNERF_OK;
+}
+
+int scatter_add_rows(const float* src, int64_t ld_src, const int64_t* idx, int64_t R, int dim,
+                     float* table, cudaStream_t st) {
+  const int64_t n = R * dim;
+  scatter_add_rows_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(src, ld_src, idx, R, dim, table);
+  UPNERF_CHECK_LAUNCH("scatter_add_rows_kernel");
+  return UPNERF_OK;
+}
+
+int ray_sum128(const void* X, int64_t ld, int64_t R, int S, float* out, int dtype, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>(ceil_div64(R, 4));
+  if (dtype == UPNERF_BF16)
+    ray_sum128_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(X), ld, R, S, out);
+  else
+    ray_sum128_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(X), ld, R, S, out);
+  UPNERF_CHECK_LAUNCH("ray_sum128_kernel");
+  return UPNERF_OK;
+}
+
+int rgb_head_bwd(const void* Q, int64_t ldq, const float* rgb, const float* d_rgb, const float* W2,
+                 int64_t R, int S, void* dQ, int64_t lddq, float* d_raybias, float* dW2, float* db2,
+                 int dtype, cudaStream_t st) {
+  int64_t blocks = ceil_div64(R, 8);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  if (dtype == UPNERF_BF16)
+    rgb_head_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(Q), ldq, rgb, d_rgb, W2, R, S, static_cast<__nv_bfloat16*>(dQ),
+        lddq, d_raybias, dW2, db2);
+  else
+    rgb_head_bwd_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<const float*>(Q), ldq, rgb, d_rgb, W2, R, S, static_cast<float*>(dQ), lddq,
+        d_raybias, dW2, db2);
+  UPNERF_CHECK_LAUNCH("rgb_head_bwd_kernel");
+  return UPNERF_OK;
+}
+
+int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N, float* out,
+                    float* out_s, int dtype, cudaStream_t st) {
+  UPNERF_REQUIRE(N >= 2 && N <= 256 && N % 2 == 0 && 256 % (N / 2) == 0, UPNERF_ERR_BAD_SHAPE,
+                 "rowscale_colsum: N=%d", N);
+  const int groups = 256 / (N / 2);
+  int64_t blocks = ceil_div64(M, groups * 8);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (dtype == UPNERF_BF16)
+    rowscale_colsum_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(X), ld, s, M, N, out, out_s);
+  else
+    rowscale_colsum_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        static_cast<const float*>(X), ld, s, M, N, out, out_s);
+  UPNERF_CHECK_LAUNCH("rowscale_colsum_kernel");
+  return UPNERF_OK;
+}
+
+int rowdot_head(const float* X, int64_t ld, int64_t M, int N, int nh, const float* w, const float* b,
+                int act, float* out, cudaStream_t st) {
+  rowdot_head_kernel<<<static_cast<unsigned>(ceil_div64(M, 4)), 128, 0, st>>>(X, ld, M, N, nh, w, b, act, out);
+  UPNERF_CHECK_LAUNCH("rowdot_head_kernel");
+  return UPNERF_OK;
+}
+
+int run_pack(const PackList& list, int dtype, cudaStream_t st) {
+  if (list.n == 0) return UPNERF_OK;
+  dim3 grid(64, list.n);
+  if (dtype == UPNERF_BF16) pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(list);
+  else pack_kernel<float><<<grid, 256, 0, st>>>(list);
+  UPNERF_CHECK_LAUNCH("pack_kernel");
+  return UPNERF_OK;
+}
+
+}  // namespace upnerf

@@ -1,0 +1,35 @@
+// Internal (non-ABI) declarations shared between the translation units of the library.
+#pragma once
+#include "common.h"
+
+namespace upnerf {
+
+// One strided copy fp32 -> T with optional transpose: dst[r, c] (or dst[c, r]) = src[r, c].
+struct PackOp {
+  const float* src;
+  int64_t ld_src;
+  void* dst;
+  int64_t ld_dst;
+  int rows, cols, transpose;
+};
+constexpr int kMaxPackOps = 40;
+struct PackList {
+  PackOp ops[kMaxPackOps];
+  int n;
+};
+
+int run_pack(const PackList& list, int dtype, cudaStream_t st);
+int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, float* out, int64_t ld_out,
+                cudaStream_t st);
+int scatter_add_rows(const float* src, int64_t ld_src, const int64_t* idx, int64_t R, int dim,
+                     float* table, cudaStream_t st);
+int ray_sum128(const void* X, int64_t ld, int64_t R, int S, float* out, int dtype, cudaStream_t st);
+int rgb_head_bwd(const void* Q, int64_t ldq, const float* rgb, const float* d_rgb, const float* W2,
+                 int64_t R, int S, void* dQ, int64_t lddq, float* d_raybias, float* dW2, float* db2,
+                 int dtype, cudaStream_t st);
+int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N, float* out,
+                    float* out_s, int dtype, cudaStream_t st);
+int rowdot_head(const float* X, int64_t ld, int64_t M, int N, int nh, const float* w, const float* b,
+                int act, float* out, cudaStream_t st);
+
+}  // namespace upnerf

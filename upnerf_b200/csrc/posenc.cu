@@ -1,0 +1,216 @@
+// Coarse-to-fine positional encoding (subsystem (b), encoding part), forward and backward.
+//
+//   upnerf_c2f_weights        models/nerf.py:137-142   w_k = (1 - cos(pi clamp(alpha-k,0,1)))/2
+//   upnerf_posenc_fwd         models/nerf.py:126-147   standalone encoding of (M,3) inputs
+//   upnerf_points_posenc_fwd  models/rendering.py:251,308 + nerf.py:126-147 fused:
+//                             x = o + d z is formed in registers and never written
+//   upnerf_points_posenc_bwd  d(encoding) -> d(rays_o), d(rays_d): the pose-gradient path
+//
+// Output row layout (width 3+6L, padded with zeros to `ld_out`):
+//   [x0 x1 x2 | for c in 0..2: w_k sin(x_c f_k) k<L, w_k cos(x_c f_k) k<L],  f_k = fp32(pi) 2^k.
+// sin/cos arguments reach ~1e4, so the full-accuracy sincosf is used (no fast-math here).
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace upnerf {
+namespace {
+
+constexpr int kMaxL = 16;
+
+__device__ __forceinline__ void store_val(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_val(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float load_val(const float* p) { return *p; }
+__device__ __forceinline__ float load_val(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+__global__ void c2f_weights_kernel(const float* __restrict__ progress, float start, float end,
+                                   int use_c2f, int L, float* __restrict__ w) {
+  const int k = threadIdx.x;
+  if (k >= L) return;
+  if (!use_c2f) {
+    w[k] = 1.f;
+    return;
+  }
+  const float kPi = 3.14159265358979323846f;
+  // same fp32 operation order as the reference: ((p - start) / (end - start)) * L
+  const float alpha = __fmul_rn(__fdiv_rn(progress[0] - start, end - start), static_cast<float>(L));
+  float t = alpha - static_cast<float>(k);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  w[k] = (1.f - cosf(__fmul_rn(t, kPi))) / 2.f;
+}
+
+template <typename T>
+__device__ __forceinline__ void encode_row(const float x[3], int L, const float* __restrict__ bw,
+                                           T* __restrict__ out, int ld_out) {
+  const float kPi = 3.14159265358979323846f;
+  store_val(out + 0, x[0]);
+  store_val(out + 1, x[1]);
+  store_val(out + 2, x[2]);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float f = kPi;
+    T* o = out + 3 + c * 2 * L;
+    for (int k = 0; k < L; ++k) {
+      float sn, cs;
+      sincosf(__fmul_rn(x[c], f), &sn, &cs);
+      const float wk = bw[k];
+      store_val(o + k, sn * wk);
+      store_val(o + L + k, cs * wk);
+      f *= 2.f;
+    }
+  }
+  for (int i = 3 + 6 * L; i < ld_out; ++i) store_val(out + i, 0.f);
+}
+
+template <typename T>
+__global__ void posenc_fwd_kernel(const float* __restrict__ x, int64_t ld_x, int64_t M, int L,
+                                  const float* __restrict__ band_w, T* __restrict__ out,
+                                  int64_t ld_row, int width) {
+  __shared__ float bw[kMaxL];
+  if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
+  __syncthreads();
+  const int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (m >= M) return;
+  const float v[3] = {x[m * ld_x], x[m * ld_x + 1], x[m * ld_x + 2]};
+  encode_row<T>(v, L, bw, out + m * ld_row, width);
+}
+
+template <typename T>
+__global__ void points_posenc_fwd_kernel(const float* __restrict__ rays, const float* __restrict__ z,
+                                         int64_t M, int S, int L, const float* __restrict__ band_w,
+                                         T* __restrict__ out, int64_t ld_row, int width) {
+  __shared__ float bw[kMaxL];
+  if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
+  __syncthreads();
+  const int64_t m = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (m >= M) return;
+  const int64_t r = m / S;
+  const float* ray = rays + r * 8;
+  const float zz = z[m];
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) v[c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+  encode_row<T>(v, L, bw, out + m * ld_row, width);
+}
+
+// One warp per ray: each lane walks samples lane, lane+32, ...; dx is reduced over the ray.
+template <typename T>
+__global__ void __launch_bounds__(128)
+points_posenc_bwd_kernel(const T* __restrict__ d_pe, int64_t ld_row, const float* __restrict__ rays,
+                         const float* __restrict__ z, int64_t R, int S, int L,
+                         const float* __restrict__ band_w, float* __restrict__ d_rays) {
+  __shared__ float bw[kMaxL];
+  if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * 4ll + warp;
+  if (r >= R) return;
+  const float kPi = 3.14159265358979323846f;
+  const float* ray = rays + r * 8;
+  float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+  for (int s = lane; s < S; s += 32) {
+    const int64_t m = r * S + s;
+    const float zz = z[m];
+    const T* g = d_pe + m * ld_row;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xc = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+      float dx = load_val(g + c);
+      float f = kPi;
+      const T* gc = g + 3 + c * 2 * L;
+      for (int k = 0; k < L; ++k) {
+        float sn, cs;
+        sincosf(__fmul_rn(xc, f), &sn, &cs);
+        dx += bw[k] * f * (cs * load_val(gc + k) - sn * load_val(gc + L + k));
+        f *= 2.f;
+      }
+      go[c] += dx;
+      gd[c] += dx * zz;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      go[c] += __shfl_xor_sync(0xffffffffu, go[c], o);
+      gd[c] += __shfl_xor_sync(0xffffffffu, gd[c], o);
+    }
+  }
+  if (lane == 0) {
+    float* out = d_rays + r * 8;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      out[c] += go[c];
+      out[3 + c] += gd[c];
+    }
+  }
+}
+
+}  // namespace
+}  // namespace upnerf
+
+extern "C" {
+
+int upnerf_c2f_weights(const float* progress_dev, float start, float end, int use_c2f, int L,
+                       float* band_w, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(L >= 1 && L <= kMaxL, UPNERF_ERR_BAD_SHAPE, "c2f_weights: L=%d", L);
+  UPNERF_REQUIRE(!use_c2f || progress_dev, UPNERF_ERR_BAD_SHAPE, "c2f_weights: progress missing");
+  c2f_weights_kernel<<<1, 32, 0, as_stream(stream)>>>(progress_dev, start, end, use_c2f, L, band_w);
+  UPNERF_CHECK_LAUNCH("c2f_weights_kernel");
+  return UPNERF_OK;
+}
+
+int upnerf_posenc_fwd(const float* x, int64_t ld_x, int64_t M, int L, const float* band_w, void* out,
+                      int64_t ld_out, int width, int dtype, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(M > 0 && L >= 1 && L <= kMaxL && width >= 3 + 6 * L && ld_out >= width,
+                 UPNERF_ERR_BAD_SHAPE, "posenc_fwd: M=%lld L=%d width=%d ld=%lld", (long long)M, L,
+                 width, (long long)ld_out);
+  const unsigned grid = static_cast<unsigned>(ceil_div64(M, 128));
+  if (dtype == UPNERF_BF16)
+    posenc_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
+        x, ld_x, M, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out, width);
+  else
+    posenc_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(x, ld_x, M, L, band_w,
+                                                                   static_cast<float*>(out), ld_out, width);
+  UPNERF_CHECK_LAUNCH("posenc_fwd_kernel");
+  return UPNERF_OK;
+}
+
+int upnerf_points_posenc_fwd(const float* rays, const float* z, int64_t n_rays, int n_samples, int L,
+                             const float* band_w, void* out, int64_t ld_out, int width, int dtype,
+                             void* stream) {
+  using namespace upnerf;
+  const int64_t M = n_rays * n_samples;
+  UPNERF_REQUIRE(M > 0 && L >= 1 && L <= kMaxL && width >= 3 + 6 * L && ld_out >= width,
+                 UPNERF_ERR_BAD_SHAPE, "points_posenc_fwd: bad sizes");
+  const unsigned grid = static_cast<unsigned>(ceil_div64(M, 128));
+  if (dtype == UPNERF_BF16)
+    points_posenc_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
+        rays, z, M, n_samples, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out, width);
+  else
+    points_posenc_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(
+        rays, z, M, n_samples, L, band_w, static_cast<float*>(out), ld_out, width);
+  UPNERF_CHECK_LAUNCH("points_posenc_fwd_kernel");
+  return UPNERF_OK;
+}
+
+int upnerf_points_posenc_bwd(const void* d_pe, int64_t ld_pe, const float* rays, const float* z,
+                             int64_t n_rays, int n_samples, int L, const float* band_w,
+                             float* d_rays, int dtype, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(n_rays > 0 && n_samples > 0 && L >= 1 && L <= kMaxL, UPNERF_ERR_BAD_SHAPE,
+                 "points_posenc_bwd: bad sizes");
+  const unsigned grid = static_cast<unsigned>(ceil_div64(n_rays, 4));
+  if (dtype == UPNERF_BF16)
+    points_posenc_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_pe), ld_pe, rays, z, n_rays, n_samples, L, band_w, d_rays);
+  else
+    points_posenc_bwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(
+        static_cast<const float*>(d_pe), ld_pe, rays, z, n_rays, n_samples, L, band_w, d_rays);
+  UPNERF_CHECK_LAUNCH("points_posenc_bwd_kernel");
+  return UPNERF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,723 @@
+// Host orchestration of the whole path: render_rays (reference models/rendering.py:53-314)
+// driving NeRF.forward (models/nerf.py:80-124) for the coarse and fine networks, forward and
+// backward, as a fixed sequence of kernel launches on one stream.
+//
+// Data flow of one network pass over M = R*S samples (T = bf16 or fp32):
+//   PE(x) --L1--> H1 .. H4 | skip [H4|PE] --L5--> H5 .. H8 --(row-dot)--> s_sigma
+//   H8 --final--> HF --(+per-ray bias)--> G1 -> G2 --(row-dot)--> c_sigma      (candidate head)
+//                  HF --(W_rgb0[:, :F] W_sf folded, +per-ray bias)--> Q --(row-dots)--> s_rgb
+//   compositing reduces {s_sigma, c_sigma, s_rgb, HF, G2} per ray; the two linear 384-d
+//   feature projections run once per RAY on the composited hidden vectors.
+// Per-ray inputs (appearance / candidate embeddings, direction encoding) enter their layers
+// as a per-ray bias, so nothing per-ray is ever repeated per sample.
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "common.h"
+#include "internal.h"
+
+namespace upnerf {
+namespace {
+
+constexpr int W = 256, H = 128, PEW = 64, X4W = 320;
+
+// ------------------------------------------------------------------ parameter layout
+struct NetLayout {
+  int in_xyz, in_dir, rgb_in, F, ad, cd;
+  int64_t progress, Wl[8], bl[8], Wf, bf, Ws, bs, Wsf, bsf, Wr0, br0, Wr2, br2;
+  int64_t Wc0, bc0, Wc2, bc2, Wcs, bcs, Wcf, bcf;
+  int64_t total;
+};
+
+int make_layout(const upnerf_net_config& c, NetLayout* L) {
+  UPNERF_REQUIRE(c.D == 8 && c.W == 256, UPNERF_ERR_BAD_CONFIG,
+                 "only the D=8, W=256, skips=[4] trunk is implemented (got D=%d W=%d)", c.D, c.W);
+  UPNERF_REQUIRE(c.xyz_L >= 1 && c.xyz_L <= 10 && c.dir_L >= 1 && c.dir_L <= 16, UPNERF_ERR_BAD_CONFIG,
+                 "xyz_L=%d (<=10) / dir_L=%d (<=16) unsupported", c.xyz_L, c.dir_L);
+  UPNERF_REQUIRE(!c.encode_feat || c.feat_dim > 0, UPNERF_ERR_BAD_CONFIG, "encode_feat needs feat_dim");
+  UPNERF_REQUIRE(c.encode_feat || c.candidate_dim == 0, UPNERF_ERR_BAD_CONFIG,
+                 "encode_feat=False with a candidate head (c_rgb path) is not implemented");
+  memset(L, 0, sizeof(*L));
+  L->in_xyz = 6 * c.xyz_L + 3;
+  L->in_dir = 6 * c.dir_L + 3;
+  L->F = c.encode_feat ? c.feat_dim : 0;
+  L->ad = c.appearance_dim;
+  L->cd = c.candidate_dim;
+  L->rgb_in = (c.encode_feat ? c.feat_dim : W) + L->in_dir + L->ad;
+  int64_t o = 0;
+  L->progress = o; o += 1;
+  for (int i = 0; i < 8; ++i) {
+    const int k = i == 0 ? L->in_xyz : (i == 4 ? W + L->in_xyz : W);
+    L->Wl[i] = o; o += static_cast<int64_t>(W) * k;
+    L->bl[i] = o; o += W;
+  }
+  L->Wf = o; o += W * W;
+  L->bf = o; o += W;
+  L->Ws = o; o += W;
+  L->bs = o; o += 1;
+  if (c.encode_feat) {
+    L->Wsf = o; o += static_cast<int64_t>(L->F) * W;
+    L->bsf = o; o += L->F;
+  }
+  L->Wr0 = o; o += static_cast<int64_t>(H) * L->rgb_in;
+  L->br0 = o; o += H;
+  L->Wr2 = o; o += 3 * H;
+  L->br2 = o; o += 3;
+  if (c.candidate_dim > 0) {
+    L->Wc0 = o; o += static_cast<int64_t>(H) * (W + L->cd);
+    L->bc0 = o; o += H;
+    L->Wc2 = o; o += H * H;
+    L->bc2 = o; o += H;
+    L->Wcs = o; o += H;
+    L->bcs = o; o += 1;
+    L->Wcf = o; o += static_cast<int64_t>(L->F) * H;
+    L->bcf = o; o += L->F;
+  }
+  L->total = o;
+  return UPNERF_OK;
+}
+
+// ------------------------------------------------------------------ workspace carving
+struct Bump {
+  uint8_t* base;
+  uint64_t off;
+  template <typename U> U* take(uint64_t count) {
+    off = (off + 255) & ~uint64_t(255);
+    U* p = base ? reinterpret_cast<U*>(base + off) : nullptr;
+    off += count * sizeof(U);
+    return p;
+  }
+  void* take_bytes(uint64_t bytes) { return take<uint8_t>(bytes); }
+};
+
+struct Packed {  // GEMM operands derived from the fp32 parameters (element type T)
+  void *W1, *Wk[8], *W5, *WF, *Wc1, *Wc2, *Wq;         // [N, K] K-major
+  void *W1T, *WkT[8], *W5T, *WFT, *Wc1T, *Wc2T, *WqT;  // transposed for the data gradient
+  float* Wq32;      // [128,256] fp32 folded rgb weight
+  float* bq_const;  // [128]
+  float* band_xyz;  // [16]
+  float* band_dir;  // [16]
+  void* region;     // start of the packed T region (zeroed before packing)
+  uint64_t region_bytes;
+};
+
+struct PassBufs {
+  int64_t R, M;
+  int S;
+  // saved by forward
+  void *X4, *Hs[9], *HF, *G1, *G2, *Q;  // Hs[1..8]; Hs[4] aliases X4 (ld 320)
+  float *ssig, *csig, *rgb, *z;
+  float *HFr, *G2r, *Wsum, *Wcsum, *P, *Crows, *Bq, *Bc;
+  Packed pk;
+};
+
+struct Scratch {
+  void *dA, *dB, *dHF, *dG2p, *dG1p, *dQp, *dPE;
+  float *dssig, *dcsig, *drgb;
+  float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
+};
+
+void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBufs* p) {
+  const int64_t M = R * S;
+  p->R = R; p->M = M; p->S = S;
+  p->X4 = b.take_bytes(M * X4W * es);
+  for (int i = 1; i <= 8; ++i) p->Hs[i] = (i == 4) ? p->X4 : b.take_bytes(M * W * es);
+  p->Hs[0] = nullptr;
+  p->HF = b.take_bytes(M * W * es);
+  p->G1 = b.take_bytes(M * H * es);
+  p->G2 = b.take_bytes(M * H * es);
+  p->Q = b.take_bytes(M * H * es);
+  p->ssig = b.take<float>(M);
+  p->csig = b.take<float>(M);
+  p->rgb = b.take<float>(M * 3);
+  p->z = b.take<float>(M);
+  p->HFr = b.take<float>(R * W);
+  p->G2r = b.take<float>(R * H);
+  p->Wsum = b.take<float>(R);
+  p->Wcsum = b.take<float>(R);
+  p->P = b.take<float>(R * (L.in_dir + L.ad));
+  p->Crows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
+  p->Bq = b.take<float>(R * H);
+  p->Bc = b.take<float>(R * H);
+  Packed& k = p->pk;
+  k.Wq32 = b.take<float>(H * W);
+  k.bq_const = b.take<float>(H);
+  k.band_xyz = b.take<float>(16);
+  k.band_dir = b.take<float>(16);
+  b.off = (b.off + 255) & ~uint64_t(255);
+  const uint64_t start = b.off;
+  k.region = b.base ? b.base + start : nullptr;
+  k.W1 = b.take_bytes(W * PEW * es);
+  k.W1T = b.take_bytes(PEW * W * es);
+  for (int i = 0; i < 8; ++i) {
+    k.Wk[i] = k.WkT[i] = nullptr;
+    if (i == 0 || i == 4) continue;
+    k.Wk[i] = b.take_bytes(W * W * es);
+    k.WkT[i] = b.take_bytes(W * W * es);
+  }
+  k.W5 = b.take_bytes(W * X4W * es);
+  k.W5T = b.take_bytes(X4W * W * es);
+  k.WF = b.take_bytes(W * W * es);
+  k.WFT = b.take_bytes(W * W * es);
+  k.Wc1 = b.take_bytes(H * W * es);
+  k.Wc1T = b.take_bytes(W * H * es);
+  k.Wc2 = b.take_bytes(H * H * es);
+  k.Wc2T = b.take_bytes(H * H * es);
+  k.Wq = b.take_bytes(H * W * es);
+  k.WqT = b.take_bytes(W * H * es);
+  k.region_bytes = b.off - start;
+}
+
+void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scratch* s) {
+  const int64_t M = R * S;
+  s->dA = b.take_bytes(M * W * es);
+  s->dB = b.take_bytes(M * W * es);
+  s->dHF = b.take_bytes(M * W * es);
+  s->dG2p = b.take_bytes(M * H * es);
+  s->dG1p = b.take_bytes(M * H * es);
+  s->dQp = b.take_bytes(M * H * es);
+  s->dPE = b.take_bytes(M * PEW * es);
+  s->dssig = b.take<float>(M);
+  s->dcsig = b.take<float>(M);
+  s->drgb = b.take<float>(M * 3);
+  s->gHFr = b.take<float>(R * W);
+  s->gG2r = b.take<float>(R * H);
+  s->gWs = b.take<float>(R);
+  s->gWc = b.take<float>(R);
+  s->dBq = b.take<float>(R * H);
+  s->dBc = b.take<float>(R * H);
+  s->dP = b.take<float>(R * (L.in_dir + L.ad));
+  s->dCrows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
+  s->dWq = b.take<float>(H * W);
+  s->dbq = b.take<float>(H);
+}
+
+struct Plan {
+  NetLayout L;
+  PassBufs coarse, fine;
+  Scratch scratch;
+  uint64_t bytes;
+  size_t es;
+  int S_f;
+};
+
+int make_plan(const upnerf_render_args& a, void* base, Plan* pl) {
+  UPNERF_TRY(make_layout(a.cfg, &pl->L));
+  UPNERF_REQUIRE(a.dtype == UPNERF_F32 || a.dtype == UPNERF_BF16, UPNERF_ERR_BAD_CONFIG, "dtype=%d", a.dtype);
+  UPNERF_REQUIRE(a.n_rays > 0 && a.n_samples >= 3 && a.n_samples <= 256 && a.n_importance >= 0 &&
+                     a.n_samples + a.n_importance <= 256,
+                 UPNERF_ERR_BAD_SHAPE, "n_rays=%lld n_samples=%d n_importance=%d unsupported",
+                 (long long)a.n_rays, a.n_samples, a.n_importance);
+  pl->es = a.dtype == UPNERF_BF16 ? 2 : 4;
+  pl->S_f = a.n_samples + a.n_importance;
+  UPNERF_REQUIRE((a.n_rays * a.n_samples) % 8 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "n_rays*n_samples must be a multiple of 8");
+  Bump b{static_cast<uint8_t*>(base), 0};
+  carve_pass(b, a.n_rays, a.n_samples, pl->es, pl->L, &pl->coarse);
+  if (a.n_importance > 0) carve_pass(b, a.n_rays, pl->S_f, pl->es, pl->L, &pl->fine);
+  carve_scratch(b, a.n_rays, a.n_importance > 0 ? pl->S_f : a.n_samples, pl->es, pl->L, &pl->scratch);
+  pl->bytes = b.off + 256;
+  return UPNERF_OK;
+}
+
+// ------------------------------------------------------------------ phase flags
+struct Phase {
+  bool cand, rgb, feat;
+  int feat_mode;
+};
+Phase make_phase(const upnerf_net_config& c, float m) {
+  Phase p;
+  p.cand = (m < 1.f) && c.encode_candidate && c.candidate_dim > 0 && c.encode_feat;
+  p.rgb = c.encode_feat ? (m > 0.f) : true;
+  p.feat = c.encode_feat && (m < 1.f);
+  p.feat_mode = !p.feat ? 0 : (p.cand ? 2 : 1);
+  return p;
+}
+
+// ------------------------------------------------------------------ GEMM dispatch by precision
+struct Ctx {
+  int dtype;
+  size_t es;
+  cudaStream_t st;
+};
+
+inline void* col(void* p, int64_t c, size_t es) { return static_cast<uint8_t*>(p) + c * es; }
+inline const void* col(const void* p, int64_t c, size_t es) { return static_cast<const uint8_t*>(p) + c * es; }
+
+// C[M,N] = epi(A[M,K] B[N,K]^T) with T operands
+int linear(const Ctx& c, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+           int64_t M, int N, int K, upnerf_epilogue ep) {
+  if (c.dtype == UPNERF_BF16) return upnerf_gemm_bf16(A, lda, B, ldb, C, ldc, M, N, K, &ep, c.st);
+  upnerf_epilogue e2 = ep;
+  e2.n_heads = 0;
+  UPNERF_TRY(upnerf_gemm_f32(static_cast<const float*>(A), lda, 1, static_cast<const float*>(B), ldb, 1,
+                             static_cast<float*>(C), ldc, 1, M, N, K, &e2, 0, 1, c.st));
+  if (ep.n_heads > 0)
+    UPNERF_TRY(rowdot_head(static_cast<const float*>(C), ldc, M, N, ep.n_heads, ep.head_w, ep.head_b,
+                           ep.head_act, ep.head_out, c.st));
+  return UPNERF_OK;
+}
+
+struct Seg { int src, len, dst; };
+
+// dW[n, map(k)] += dY^T X ; db[n] += colsum(dY)
+int wgrad(const Ctx& c, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+          float* db, int64_t M, int N, int K, const Seg* segs, int nseg) {
+  if (c.dtype == UPNERF_BF16) {
+    int src[4], len[4], dst[4];
+    for (int i = 0; i < nseg; ++i) { src[i] = segs[i].src; len[i] = segs[i].len; dst[i] = segs[i].dst; }
+    return upnerf_wgrad_bf16(dY, lddy, X, ldx, dW, lddw, db, M, N, K, nseg, src, len, dst, c.st);
+  }
+  const float* y = static_cast<const float*>(dY);
+  const float* x = static_cast<const float*>(X);
+  for (int i = 0; i < nseg; ++i) {
+    const int64_t tiles = ceil_div64(N, 64) * ceil_div64(segs[i].len, 64);
+    int split = static_cast<int>(ceil_div64(4 * sm_count(), tiles));
+    const int64_t maxsplit = ceil_div64(M, 256);
+    if (split > maxsplit) split = static_cast<int>(maxsplit);
+    if (split < 2) split = 2;  // split_k >= 2 selects the atomic accumulate path
+    UPNERF_TRY(upnerf_gemm_f32(y, 1, lddy, x + segs[i].src, 1, ldx, dW + segs[i].dst, lddw, 1, N,
+                               segs[i].len, M, nullptr, 0, split, c.st));
+  }
+  if (db) UPNERF_TRY(rowscale_colsum(dY, lddy, nullptr, M, N, db, nullptr, c.dtype, c.st));
+  return UPNERF_OK;
+}
+
+// small fp32 product with arbitrary strides (per-ray work and parameter-space chain rules)
+int mm(const Ctx& c, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+       float* C, int64_t scm, int64_t scn, int64_t M, int64_t N, int64_t K, const upnerf_epilogue* ep,
+       int accumulate, int split_k = 1) {
+  return upnerf_gemm_f32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
+}
+int split_for(int64_t K) {
+  int64_t s = ceil_div64(K, 512);
+  if (s < 2) s = 2;
+  if (s > 256) s = 256;
+  return static_cast<int>(s);
+}
+
+upnerf_epilogue ep_none() {
+  upnerf_epilogue e;
+  memset(&e, 0, sizeof(e));
+  return e;
+}
+
+// ------------------------------------------------------------------ weight packing
+int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L, const Phase& ph,
+                 const float* prm, Packed& k) {
+  UPNERF_CHECK_CUDA(cudaMemsetAsync(k.region, 0, k.region_bytes, c.st));
+  UPNERF_TRY(upnerf_c2f_weights(prm + L.progress, cfg.c2f_start, cfg.c2f_end, cfg.use_c2f, cfg.xyz_L,
+                                k.band_xyz, c.st));
+  UPNERF_TRY(upnerf_c2f_weights(prm + L.progress, cfg.c2f_start, cfg.c2f_end, cfg.use_c2f, cfg.dir_L,
+                                k.band_dir, c.st));
+  PackList pl;
+  pl.n = 0;
+  auto add = [&](const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int rows, int cols, int tr) {
+    pl.ops[pl.n++] = PackOp{src, ld_src, dst, ld_dst, rows, cols, tr};
+  };
+  const int ix = L.in_xyz;
+  // layer 1: [256, in_xyz] -> [256, 64] (zero padded) and its transpose [64, 256]
+  add(prm + L.Wl[0], ix, k.W1, PEW, W, ix, 0);
+  add(prm + L.Wl[0], ix, k.W1T, W, W, ix, 1);
+  for (int i = 1; i < 8; ++i) {
+    if (i == 4) continue;
+    add(prm + L.Wl[i], W, k.Wk[i], W, W, W, 0);
+    add(prm + L.Wl[i], W, k.WkT[i], W, W, W, 1);
+  }
+  // skip layer: reference input is [PE | h]; the packed input is [h | PE | 0]
+  add(prm + L.Wl[4] + ix, W + ix, k.W5, X4W, W, W, 0);
+  add(prm + L.Wl[4], W + ix, col(k.W5, W, c.es), X4W, W, ix, 0);
+  add(prm + L.Wl[4] + ix, W + ix, k.W5T, W, W, W, 1);
+  add(prm + L.Wl[4], W + ix, col(k.W5T, static_cast<int64_t>(W) * W, c.es), W, W, ix, 1);
+  add(prm + L.Wf, W, k.WF, W, W, W, 0);
+  add(prm + L.Wf, W, k.WFT, W, W, W, 1);
+  if (ph.cand) {
+    add(prm + L.Wc0, W + L.cd, k.Wc1, W, H, W, 0);
+    add(prm + L.Wc0, W + L.cd, k.Wc1T, H, H, W, 1);
+    add(prm + L.Wc2, H, k.Wc2, H, H, H, 0);
+    add(prm + L.Wc2, H, k.Wc2T, H, H, H, 1);
+  }
+  if (ph.rgb) {
+    if (cfg.encode_feat) {
+      // Wq = W_rgb0[:, :F] W_sf  (128 x 256);  bq_const = W_rgb0[:, :F] b_sf + b_rgb0
+      UPNERF_TRY(mm(c, prm + L.Wr0, L.rgb_in, 1, prm + L.Wsf, 1, W, k.Wq32, W, 1, H, W, L.F, nullptr, 0));
+      upnerf_epilogue e = ep_none();
+      e.bias = prm + L.br0;
+      UPNERF_TRY(mm(c, prm + L.bsf, 0, 1, prm + L.Wr0, L.rgb_in, 1, k.bq_const, 0, 1, 1, H, L.F, &e, 0));
+      add(k.Wq32, W, k.Wq, W, H, W, 0);
+      add(k.Wq32, W, k.WqT, H, H, W, 1);
+    } else {
+      UPNERF_CHECK_CUDA(cudaMemcpyAsync(k.bq_const, prm + L.br0, H * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, c.st));
+      add(prm + L.Wr0, L.rgb_in, k.Wq, W, H, W, 0);
+      add(prm + L.Wr0, L.rgb_in, k.WqT, H, H, W, 1);
+    }
+  }
+  return run_pack(pl, c.dtype, c.st);
+}
+
+// ------------------------------------------------------------------ one network, forward
+int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
+             const upnerf_pass_io& io, PassBufs& p) {
+  const upnerf_net_config& cfg = a.cfg;
+  const float* prm = io.params;
+  const int64_t M = p.M, R = p.R;
+  const int S = p.S;
+  Packed& k = p.pk;
+  UPNERF_TRY(pack_weights(c, cfg, L, ph, prm, k));
+
+  // positional encoding of x = o + d z straight into the skip buffer [H4 | PE]
+  void* PE = col(p.X4, W, c.es);
+  UPNERF_TRY(upnerf_points_posenc_fwd(a.rays, p.z, R, S, cfg.xyz_L, k.band_xyz, PE, X4W, PEW, c.dtype, c.st));
+
+  // trunk
+  upnerf_epilogue e = ep_none();
+  e.act = 1;
+  e.bias = prm + L.bl[0];
+  UPNERF_TRY(linear(c, PE, X4W, k.W1, PEW, p.Hs[1], W, M, W, PEW, e));
+  for (int i = 1; i < 8; ++i) {
+    e = ep_none();
+    e.act = 1;
+    e.bias = prm + L.bl[i];
+    const void* in = p.Hs[i];
+    const int64_t ldin = (i == 4) ? X4W : W;
+    void* out = p.Hs[i + 1];
+    const int64_t ldout = (i + 1 == 4) ? X4W : W;
+    if (i == 7) {  // share_sigma rides on layer 8's epilogue
+      e.n_heads = 1;
+      e.head_w = prm + L.Ws;
+      e.head_b = prm + L.bs;
+      e.head_act = 1;
+      e.head_out = p.ssig;
+    }
+    if (i == 4) UPNERF_TRY(linear(c, in, ldin, k.W5, X4W, out, ldout, M, W, X4W, e));
+    else UPNERF_TRY(linear(c, in, ldin, k.Wk[i], W, out, ldout, M, W, W, e));
+  }
+  // xyz_encoding_final (no activation)
+  e = ep_none();
+  e.bias = prm + L.bf;
+  UPNERF_TRY(linear(c, p.Hs[8], W, k.WF, W, p.HF, W, M, W, W, e));
+
+  if (ph.cand) {
+    // per-ray bias of candidate_encoding.0: W[:, 256:] c_emb + b
+    UPNERF_TRY(gather_rows(io.emb_c, a.img_idx, R, L.cd, p.Crows, L.cd, c.st));
+    e = ep_none();
+    e.bias = prm + L.bc0;
+    UPNERF_TRY(mm(c, p.Crows, L.cd, 1, prm + L.Wc0 + W, W + L.cd, 1, p.Bc, H, 1, R, H, L.cd, &e, 0));
+    e = ep_none();
+    e.act = 1;
+    e.ray_bias = p.Bc;
+    e.rows_per_ray = S;
+    UPNERF_TRY(linear(c, p.HF, W, k.Wc1, W, p.G1, H, M, H, W, e));
+    e = ep_none();
+    e.act = 1;
+    e.bias = prm + L.bc2;
+    e.n_heads = 1;
+    e.head_w = prm + L.Wcs;
+    e.head_b = prm + L.bcs;
+    e.head_act = 1;
+    e.head_out = p.csig;
+    UPNERF_TRY(linear(c, p.G1, H, k.Wc2, H, p.G2, H, M, H, H, e));
+  }
+  if (ph.rgb) {
+    // per-ray bias of rgb_share_layer.0: W[:, F:] [PE(dir) | a_emb] + (W[:, :F] b_sf + b)
+    const int pw = L.in_dir + L.ad;
+    UPNERF_TRY(upnerf_posenc_fwd(a.rays + 3, 8, R, cfg.dir_L, k.band_dir, p.P, pw, L.in_dir, UPNERF_F32, c.st));
+    if (L.ad > 0) {
+      if (cfg.encode_appearance) UPNERF_TRY(gather_rows(io.emb_a, a.img_idx, R, L.ad, p.P + L.in_dir, pw, c.st));
+      else UPNERF_REQUIRE(false, UPNERF_ERR_BAD_CONFIG, "appearance_dim > 0 with encode_appearance off");
+    }
+    const int front = cfg.encode_feat ? L.F : W;
+    e = ep_none();
+    e.bias = k.bq_const;
+    UPNERF_TRY(mm(c, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, p.Bq, H, 1, R, H, pw, &e, 0));
+    e = ep_none();
+    e.act = 1;
+    e.ray_bias = p.Bq;
+    e.rows_per_ray = S;
+    e.n_heads = 3;
+    e.head_w = prm + L.Wr2;
+    e.head_b = prm + L.br2;
+    e.head_act = 2;
+    e.head_out = p.rgb;
+    UPNERF_TRY(linear(c, p.HF, W, k.Wq, W, p.Q, H, M, H, W, e));
+  }
+
+  // compositing
+  upnerf_composite_args ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.R = R; ca.S = S;
+  ca.cand = ph.cand; ca.stat_rgb = ph.rgb; ca.feat_mode = ph.feat_mode; ca.dtype = c.dtype;
+  ca.z = p.z; ca.s_sigma = p.ssig; ca.c_sigma = p.csig; ca.rgb = p.rgb;
+  ca.hf = p.HF; ca.ld_hf = W; ca.g2 = p.G2; ca.ld_g2 = H;
+  ca.c_weights = io.c_weights; ca.s_weights = io.s_weights; ca.c_depth = io.c_depth;
+  ca.t_weight = io.t_weight; ca.s_depth = io.s_depth; ca.s_rgb = io.s_rgb;
+  ca.hf_ray = p.HFr; ca.g2_ray = p.G2r; ca.ws_sum = p.Wsum; ca.wc_sum = p.Wcsum;
+  UPNERF_TRY(upnerf_composite_fwd(&ca, c.st));
+
+  if (ph.feat) {
+    // feat = W_sf (sum w hF) + b_sf sum w  [+ W_cf (sum w' g2) + b_cf sum w']
+    UPNERF_REQUIRE(io.feat, UPNERF_ERR_BAD_SHAPE, "feat output missing");
+    e = ep_none();
+    e.rank1_row = p.Wsum;
+    e.rank1_col = prm + L.bsf;
+    UPNERF_TRY(mm(c, p.HFr, W, 1, prm + L.Wsf, W, 1, io.feat, L.F, 1, R, L.F, W, &e, 0));
+    if (ph.cand) {
+      e = ep_none();
+      e.rank1_row = p.Wcsum;
+      e.rank1_col = prm + L.bcf;
+      UPNERF_TRY(mm(c, p.G2r, H, 1, prm + L.Wcf, H, 1, io.feat, L.F, 1, R, L.F, H, &e, 1));
+    }
+  }
+  return UPNERF_OK;
+}
+
+// ------------------------------------------------------------------ one network, backward
+int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
+             const upnerf_pass_io& io, PassBufs& p, Scratch& s) {
+  const upnerf_net_config& cfg = a.cfg;
+  const float* prm = io.params;
+  float* g = io.d_params;
+  UPNERF_REQUIRE(g, UPNERF_ERR_BAD_SHAPE, "render_bwd: d_params missing");
+  const int64_t M = p.M, R = p.R;
+  const int S = p.S;
+  Packed& k = p.pk;
+  upnerf_epilogue e;
+
+  // 1. per-ray feature projections
+  UPNERF_REQUIRE(!ph.feat || io.g_feat, UPNERF_ERR_BAD_SHAPE,
+                 "render_bwd: g_feat is required in this phase (pass zeros when unused)");
+  if (ph.feat) {
+    const float* gf = io.g_feat;
+    UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wsf, 1, W, s.gHFr, W, 1, R, W, L.F, nullptr, 0));
+    UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.bsf, 0, 1, s.gWs, 1, 0, R, 1, L.F, nullptr, 0));
+    UPNERF_TRY(mm(c, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
+    UPNERF_TRY(mm(c, p.Wsum, 0, 1, gf, 1, L.F, g + L.bsf, 0, 1, 1, L.F, R, nullptr, 0, split_for(R)));
+    if (ph.cand) {
+      UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wcf, 1, H, s.gG2r, H, 1, R, H, L.F, nullptr, 0));
+      UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.bcf, 0, 1, s.gWc, 1, 0, R, 1, L.F, nullptr, 0));
+      UPNERF_TRY(mm(c, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(mm(c, p.Wcsum, 0, 1, gf, 1, L.F, g + L.bcf, 0, 1, 1, L.F, R, nullptr, 0, split_for(R)));
+    }
+  }
+  const bool feat_grad = ph.feat;
+
+  // 2. compositing backward
+  upnerf_composite_args ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.R = R; ca.S = S;
+  ca.cand = ph.cand; ca.stat_rgb = ph.rgb; ca.dtype = c.dtype;
+  ca.feat_mode = feat_grad ? ph.feat_mode : 0;
+  ca.z = p.z; ca.s_sigma = p.ssig; ca.c_sigma = p.csig; ca.rgb = p.rgb;
+  ca.hf = p.HF; ca.ld_hf = W; ca.g2 = p.G2; ca.ld_g2 = H;
+  ca.g_c_weights = io.g_c_weights; ca.g_s_weights = io.g_s_weights; ca.g_c_depth = io.g_c_depth;
+  ca.g_t_weight = io.g_t_weight; ca.g_s_depth = io.g_s_depth; ca.g_s_rgb = io.g_s_rgb;
+  ca.g_hf_ray = s.gHFr; ca.g_g2_ray = s.gG2r; ca.g_ws_sum = s.gWs; ca.g_wc_sum = s.gWc;
+  ca.w_csigma = prm + L.Wcs;
+  ca.d_ssig_pre = s.dssig; ca.d_csig_pre = s.dcsig; ca.d_rgb = s.drgb;
+  ca.d_hf = s.dHF; ca.ld_dhf = W; ca.d_g2pre = s.dG2p; ca.ld_dg2 = H;
+  UPNERF_TRY(upnerf_composite_bwd(&ca, c.st));
+  bool dhf_live = feat_grad;          // does dHF hold a gradient yet?
+  bool dg2_from_feat = feat_grad && ph.cand;
+
+  // 3. rgb head
+  if (ph.rgb) {
+    UPNERF_TRY(rgb_head_bwd(p.Q, H, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H, s.dBq, g + L.Wr2,
+                            g + L.br2, c.dtype, c.st));
+    // dHF (+)= dQp Wq
+    e = ep_none();
+    if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
+    UPNERF_TRY(linear(c, s.dQp, H, k.WqT, H, s.dHF, W, M, W, H, e));
+    dhf_live = true;
+    const int pw = L.in_dir + L.ad;
+    const int front = cfg.encode_feat ? L.F : W;
+    // per-ray bias path: [PE(dir) | a_emb] columns of rgb_share_layer.0 and the appearance table
+    UPNERF_TRY(mm(c, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
+    if (L.ad > 0 && io.d_emb_a) {
+      UPNERF_TRY(mm(c, s.dBq, H, 1, prm + L.Wr0 + front + L.in_dir, 1, L.rgb_in, s.dP, L.ad, 1, R, L.ad, H, nullptr, 0));
+      UPNERF_TRY(scatter_add_rows(s.dP, L.ad, a.img_idx, R, L.ad, io.d_emb_a, c.st));
+    }
+    UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dbq, 0, H * sizeof(float), c.st));
+    UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, s.dbq, nullptr, UPNERF_F32, c.st));
+    UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, c.st));
+    if (cfg.encode_feat) {
+      // weight gradient of the folded matrix, then the chain rule into W_rgb0[:, :F] and W_sf
+      UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
+      const Seg sg{0, W, 0};
+      UPNERF_TRY(wgrad(c, s.dQp, H, p.HF, W, s.dWq, W, nullptr, M, H, W, &sg, 1));
+      UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
+      UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
+      // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
+      UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
+      UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
+    } else {
+      const Seg sg{0, W, 0};
+      UPNERF_TRY(wgrad(c, s.dQp, H, p.HF, W, g + L.Wr0, L.rgb_in, nullptr, M, H, W, &sg, 1));
+    }
+  }
+
+  // 4. candidate head
+  if (ph.cand) {
+    UPNERF_REQUIRE(dg2_from_feat, UPNERF_ERR_BAD_CONFIG, "candidate head without the feature path");
+    // candidate_sigma: dw += sum dcsig g2, db += sum dcsig
+    UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, c.st));
+    const Seg sgH{0, H, 0};
+    UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
+    e = ep_none();
+    e.aux = p.G1; e.ldaux = H; e.aux_mode = 2;
+    UPNERF_TRY(linear(c, s.dG2p, H, k.Wc2T, H, s.dG1p, H, M, H, H, e));
+    const Seg sgW{0, W, 0};
+    UPNERF_TRY(wgrad(c, s.dG1p, H, p.HF, W, g + L.Wc0, W + L.cd, nullptr, M, H, W, &sgW, 1));
+    UPNERF_TRY(ray_sum128(s.dG1p, H, R, S, s.dBc, c.dtype, c.st));
+    UPNERF_TRY(mm(c, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
+    UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, c.st));
+    if (io.d_emb_c) {
+      UPNERF_TRY(mm(c, s.dBc, H, 1, prm + L.Wc0 + W, 1, W + L.cd, s.dCrows, L.cd, 1, R, L.cd, H, nullptr, 0));
+      UPNERF_TRY(scatter_add_rows(s.dCrows, L.cd, a.img_idx, R, L.cd, io.d_emb_c, c.st));
+    }
+    e = ep_none();
+    if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
+    UPNERF_TRY(linear(c, s.dG1p, H, k.Wc1T, H, s.dHF, W, M, W, H, e));
+    dhf_live = true;
+  }
+
+  // 5. xyz_encoding_final + share_sigma  ->  dH8_pre
+  UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, c.st));
+  void* dcur = s.dA;
+  void* dnext = s.dB;
+  if (dhf_live) {
+    const Seg sgW{0, W, 0};
+    UPNERF_TRY(wgrad(c, s.dHF, W, p.Hs[8], W, g + L.Wf, W, g + L.bf, M, W, W, &sgW, 1));
+    e = ep_none();
+    e.rank1_row = s.dssig; e.rank1_col = prm + L.Ws;
+    e.aux = p.Hs[8]; e.ldaux = W; e.aux_mode = 2;
+    UPNERF_TRY(linear(c, s.dHF, W, k.WFT, W, dcur, W, M, W, W, e));
+  } else {
+    UPNERF_REQUIRE(false, UPNERF_ERR_BAD_CONFIG, "backward without any gradient into xyz_encoding_final");
+  }
+
+  // 6. trunk, layers 8..1
+  const void* PE = col(p.X4, W, c.es);
+  bool dpe_live = false;
+  for (int i = 7; i >= 0; --i) {
+    // dcur = dH_{i+1}_pre ; input of layer i+1 is Hs[i] (or PE for i == 0, X4 for i == 4)
+    if (i == 4) {
+      const Seg sg[2] = {{0, W, L.in_xyz}, {W, L.in_xyz, 0}};
+      UPNERF_TRY(wgrad(c, dcur, W, p.X4, X4W, g + L.Wl[4], W + L.in_xyz, g + L.bl[4], M, W, X4W, sg, 2));
+      e = ep_none();
+      e.aux = p.X4; e.ldaux = X4W; e.aux_mode = 2;
+      UPNERF_TRY(linear(c, dcur, W, k.W5T, W, dnext, W, M, W, W, e));
+      e = ep_none();
+      UPNERF_TRY(linear(c, dcur, W, col(k.W5T, static_cast<int64_t>(W) * W, c.es), W, s.dPE, PEW, M, PEW, W, e));
+      dpe_live = true;
+    } else if (i == 0) {
+      const Seg sg{0, L.in_xyz, 0};
+      UPNERF_TRY(wgrad(c, dcur, W, PE, X4W, g + L.Wl[0], L.in_xyz, g + L.bl[0], M, W, PEW, &sg, 1));
+      if (a.d_rays) {
+        e = ep_none();
+        if (dpe_live) { e.aux = s.dPE; e.ldaux = PEW; e.aux_mode = 1; }
+        UPNERF_TRY(linear(c, dcur, W, k.W1T, W, s.dPE, PEW, M, PEW, W, e));
+      }
+      break;
+    } else {
+      const int64_t ldin = (i == 4) ? X4W : W;
+      const Seg sg{0, W, 0};
+      UPNERF_TRY(wgrad(c, dcur, W, p.Hs[i], ldin, g + L.Wl[i], W, g + L.bl[i], M, W, W, &sg, 1));
+      e = ep_none();
+      e.aux = p.Hs[i]; e.ldaux = ldin; e.aux_mode = 2;
+      UPNERF_TRY(linear(c, dcur, W, k.WkT[i], W, dnext, W, M, W, W, e));
+    }
+    void* t = dcur; dcur = dnext; dnext = t;
+  }
+
+  // 7. positional encoding backward -> ray gradients
+  if (a.d_rays)
+    UPNERF_TRY(upnerf_points_posenc_bwd(s.dPE, PEW, a.rays, p.z, R, S, cfg.xyz_L, k.band_xyz, a.d_rays,
+                                        c.dtype, c.st));
+  return UPNERF_OK;
+}
+
+int check_common(const upnerf_render_args& a) {
+  UPNERF_REQUIRE(upnerf_device_ok(), UPNERF_ERR_CUDA,
+                 "upnerf_b200 needs a compute-capability 10.x GPU (sm_100a); there is no fallback");
+  UPNERF_REQUIRE(a.rays && a.img_idx && a.coarse.params, UPNERF_ERR_BAD_SHAPE, "render: rays/img_idx/params missing");
+  UPNERF_REQUIRE(a.n_importance == 0 || a.fine.params, UPNERF_ERR_BAD_SHAPE, "render: fine params missing");
+  UPNERF_REQUIRE(a.workspace, UPNERF_ERR_WORKSPACE, "render: workspace missing");
+  return UPNERF_OK;
+}
+
+}  // namespace
+}  // namespace upnerf
+
+extern "C" {
+
+int64_t upnerf_nerf_param_count(const upnerf_net_config* cfg) {
+  upnerf::NetLayout L;
+  if (upnerf::make_layout(*cfg, &L) != 0) return -1;
+  return L.total;
+}
+
+uint64_t upnerf_render_workspace_bytes(const upnerf_render_args* a) {
+  upnerf::Plan pl;
+  if (upnerf::make_plan(*a, nullptr, &pl) != 0) return 0;
+  return pl.bytes;
+}
+
+int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
+  using namespace upnerf;
+  UPNERF_TRY(check_common(*a));
+  Plan pl;
+  UPNERF_TRY(make_plan(*a, a->workspace, &pl));
+  UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE,
+                 "workspace too small: %llu < %llu bytes", (unsigned long long)a->workspace_bytes,
+                 (unsigned long long)pl.bytes);
+  Ctx c{a->dtype, pl.es, as_stream(stream)};
+  const Phase ph = make_phase(a->cfg, a->sched_mult);
+  const int64_t R = a->n_rays;
+  const int S = a->n_samples;
+
+  UPNERF_TRY(upnerf_stratified_z(a->rays, a->perturb_rand, a->perturb, a->use_disp, R, S, pl.coarse.z, c.st));
+  if (a->z_coarse)
+    UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_coarse, pl.coarse.z, R * S * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->coarse, pl.coarse));
+  if (a->n_importance == 0) return UPNERF_OK;
+
+  // hierarchical resampling (models/rendering.py:262-307)
+  const float* w0 = nullptr;
+  const float* w1 = nullptr;
+  int n0 = a->n_importance, n1 = 0;
+  const bool cand_fine = a->cfg.encode_candidate && a->cfg.candidate_dim > 0;
+  if (cand_fine && a->sched_mult == 0.f) {
+    w0 = a->coarse.c_weights;
+  } else if (cand_fine && a->sched_mult > 0.f && a->sched_mult < 1.f) {
+    n1 = a->n_importance_static;
+    n0 = a->n_importance - n1;
+    w0 = a->coarse.c_weights;
+    w1 = a->coarse.s_weights;
+  } else {
+    w0 = a->coarse.s_weights;
+  }
+  UPNERF_REQUIRE(w0 && (n1 == 0 || w1), UPNERF_ERR_BAD_SHAPE, "render_fwd: coarse weights output missing");
+  UPNERF_REQUIRE(n0 >= 0 && n1 >= 0, UPNERF_ERR_BAD_SHAPE, "render_fwd: bad importance split");
+  UPNERF_TRY(upnerf_resample_merge(pl.coarse.z, w0 + 1, w1 ? w1 + 1 : nullptr, S, a->u0, a->u1, n0, n1, R, S,
+                                   1e-5f, pl.fine.z, c.st));
+  if (a->z_fine)
+    UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_fine, pl.fine.z, R * pl.S_f * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
+  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->fine, pl.fine));
+  return UPNERF_OK;
+}
+
+int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
+  using namespace upnerf;
+  UPNERF_TRY(check_common(*a));
+  Plan pl;
+  UPNERF_TRY(make_plan(*a, a->workspace, &pl));
+  UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE, "workspace too small");
+  Ctx c{a->dtype, pl.es, as_stream(stream)};
+  const Phase ph = make_phase(a->cfg, a->sched_mult);
+  if (a->n_importance > 0) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch));
+  UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch));
+  return UPNERF_OK;
+}
+
+}  // extern "C"
