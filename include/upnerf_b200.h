@@ -43,6 +43,14 @@ int upnerf_version(void);
 /* 1 if the current device is compute capability 10.x (tcgen05 available). */
 int upnerf_device_ok(void);
 
+/* Launch accounting for bench.py: total kernels launched by this library in the process,
+ * and (while enabled) CUDA-event device time / launches / declared work per kernel family:
+ * 0 gemm_tc, 1 wgrad_tc, 2 gemm_simt, 3 composite, 4 posenc, 5 sampling, 6 pose_rays,
+ * 7 heads, 8 pack.  work = 2*M*N*K flop for the GEMM families, 0 otherwise. */
+long long upnerf_launch_count(void);
+void upnerf_profile_enable(int on);
+int upnerf_profile_collect(double* ms, long long* launches, double* work, int ncat);
+
 /* ------------------------------------------------------------------------------------
  * Dense layer primitive (the "one dense contraction" of the path).
  * Replaces nn.Linear (+ReLU/Softplus/Sigmoid) calls of NeRF.forward
@@ -113,6 +121,22 @@ int upnerf_pose_rays_fwd(const float* se3_table, const int64_t* img_idx, const f
 int upnerf_pose_rays_bwd(const float* se3_table, const int64_t* img_idx, const float* c2w,
                          int c2w_is_single, const float* directions, int64_t n_rays,
                          const float* d_rays, float* d_se3_table, void* stream);
+
+/* Stand-alone pieces at the reference's own granularity (each differentiable on its own):
+ *   upnerf_se3_exp_*       Lie.se3_to_SE3   (utils/camera.py:87-98): wu [n,6] -> pose [n,3,4]
+ *   upnerf_pose_compose_*  Pose.compose_pair (utils/camera.py:51-58): out = b o a; a pose given
+ *                          as one (3,4) matrix broadcasts (x_is_single); d_a / d_b are [n,3,4]
+ *                          (NULL to skip; a broadcast operand's gradient is not reduced here)
+ *   upnerf_get_rays_bwd    gradient of get_rays (utils/ray.py:30-67) w.r.t. the pose(s):
+ *                          d_c2w [n,3,4], or one [3,4] accumulated over rays when single. */
+int upnerf_se3_exp_fwd(const float* wu, int64_t n, float* pose_out, void* stream);
+int upnerf_se3_exp_bwd(const float* wu, const float* d_pose, int64_t n, float* d_wu, void* stream);
+int upnerf_pose_compose_fwd(const float* pose_a, int a_is_single, const float* pose_b, int b_is_single,
+                            int64_t n, float* out, void* stream);
+int upnerf_pose_compose_bwd(const float* pose_a, int a_is_single, const float* pose_b, int b_is_single,
+                            const float* d_out, int64_t n, float* d_a, float* d_b, void* stream);
+int upnerf_get_rays_bwd(const float* c2w, int c2w_is_single, const float* directions, int64_t n_rays,
+                        const float* d_rays, float* d_c2w, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (d) Depth sampling.  models/rendering.py:231-249 (stratified), :7-50 (sample_pdf),

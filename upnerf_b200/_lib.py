@@ -285,3 +285,28 @@ def points_posenc_bwd(d_pe, ld_pe, rays, z, L, band_w, d_rays, dtype):
     st = lib().upnerf_points_posenc_bwd(ptr(d_pe), _i64(ld_pe), ptr(rays), ptr(z), _i64(R), C.c_int(S), C.c_int(L),
                                         ptr(band_w), ptr(d_rays), C.c_int(dtype), stream_ptr())
     check(st, "upnerf_points_posenc_bwd")
+
+
+def se3_exp_fwd(wu, out):
+    check(lib().upnerf_se3_exp_fwd(ptr(wu), _i64(wu.shape[0]), ptr(out), stream_ptr()), "upnerf_se3_exp_fwd")
+
+
+def se3_exp_bwd(wu, d_pose, d_wu):
+    check(lib().upnerf_se3_exp_bwd(ptr(wu), ptr(d_pose), _i64(wu.shape[0]), ptr(d_wu), stream_ptr()),
+          "upnerf_se3_exp_bwd")
+
+
+def pose_compose_fwd(a, a_single, b, b_single, n, out):
+    check(lib().upnerf_pose_compose_fwd(ptr(a), C.c_int(int(a_single)), ptr(b), C.c_int(int(b_single)), _i64(n),
+                                        ptr(out), stream_ptr()), "upnerf_pose_compose_fwd")
+
+
+def pose_compose_bwd(a, a_single, b, b_single, d_out, n, d_a, d_b):
+    check(lib().upnerf_pose_compose_bwd(ptr(a), C.c_int(int(a_single)), ptr(b), C.c_int(int(b_single)), ptr(d_out),
+                                        _i64(n), ptr(d_a), ptr(d_b), stream_ptr()), "upnerf_pose_compose_bwd")
+
+
+def get_rays_bwd(c2w, directions, d_rays, d_c2w):
+    single = 1 if c2w.dim() == 2 else 0
+    check(lib().upnerf_get_rays_bwd(ptr(c2w), C.c_int(single), ptr(directions), _i64(directions.shape[0]),
+                                    ptr(d_rays), ptr(d_c2w), stream_ptr()), "upnerf_get_rays_bwd")

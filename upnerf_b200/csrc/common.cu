@@ -63,9 +63,72 @@ int sm_count() {
   return n;
 }
 
+// ------------------------------------------------------------------ launch accounting
+namespace {
+constexpr int kMaxProf = 16384;
+struct Prof {
+  bool enabled = false;
+  int n = 0;
+  cudaEvent_t beg[kMaxProf], end[kMaxProf];
+  bool made[kMaxProf] = {};
+  int cat[kMaxProf];
+  double work[kMaxProf];
+};
+Prof g_prof;
+long long g_launches = 0;
+}  // namespace
+
+LaunchScope::LaunchScope(int cat, cudaStream_t stream, double work) : slot(-1), st(stream) {
+  ++g_launches;
+  if (!g_prof.enabled || g_prof.n >= kMaxProf) return;
+  slot = g_prof.n++;
+  if (!g_prof.made[slot]) {
+    cudaEventCreate(&g_prof.beg[slot]);
+    cudaEventCreate(&g_prof.end[slot]);
+    g_prof.made[slot] = true;
+  }
+  g_prof.cat[slot] = cat;
+  g_prof.work[slot] = work;
+  cudaEventRecord(g_prof.beg[slot], st);
+}
+LaunchScope::~LaunchScope() {
+  if (slot >= 0) cudaEventRecord(g_prof.end[slot], st);
+}
+
 }  // namespace upnerf
 
 extern "C" {
+
+long long upnerf_launch_count(void) { return upnerf::g_launches; }
+
+void upnerf_profile_enable(int on) {
+  upnerf::g_prof.enabled = on != 0;
+  upnerf::g_prof.n = 0;
+}
+
+// Sums event-measured device time (ms), launch counts and declared work (flop or bytes) per
+// kernel family since upnerf_profile_enable(1); synchronises on the recorded events.
+int upnerf_profile_collect(double* ms, long long* launches, double* work, int ncat) {
+  using namespace upnerf;
+  for (int i = 0; i < ncat; ++i) {
+    ms[i] = 0;
+    launches[i] = 0;
+    work[i] = 0;
+  }
+  for (int i = 0; i < g_prof.n; ++i) {
+    if (cudaEventSynchronize(g_prof.end[i]) != cudaSuccess) return UPNERF_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.beg[i], g_prof.end[i]) != cudaSuccess) return UPNERF_ERR_CUDA;
+    const int c = g_prof.cat[i];
+    if (c < ncat) {
+      ms[c] += t;
+      launches[c] += 1;
+      work[c] += g_prof.work[i];
+    }
+  }
+  g_prof.n = 0;
+  return UPNERF_OK;
+}
 
 const char* upnerf_last_error(void) { return upnerf::g_err; }
 

@@ -47,6 +47,20 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 int sm_count();
 
+// Launch accounting.  Every kernel launcher opens a LaunchScope: it bumps the library-wide
+// launch counter and, while profiling is enabled, brackets the launch with CUDA events on
+// the launching stream so that bench.py can attribute device time to kernel families.
+enum LaunchCat {
+  kCatGemmTc = 0, kCatWgradTc, kCatGemmSimt, kCatComposite, kCatPosenc, kCatSampling,
+  kCatPoseRays, kCatHeads, kCatPack, kNumCats
+};
+struct LaunchScope {
+  int slot;
+  cudaStream_t st;
+  LaunchScope(int cat, cudaStream_t stream, double work = 0.0);
+  ~LaunchScope();
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const CompAr
   T* dhf = static_cast<T*>(p.d_hf) + r * S * p.ld_dhf;
   T* dg2 = p.cand ? static_cast<T*>(p.d_g2pre) + r * S * p.ld_dg2 : nullptr;
   float wcs[4] = {0.f, 0.f, 0.f, 0.f};
-  if (p.cand) Vec<float>::load<4>(p.w_csigma, lane, wcs);
+  if (p.cand) {  // parameter pointer: only 4-byte aligned inside the flat buffer
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wcs[e] = __ldg(p.w_csigma + lane * 4 + e);
+  }
   for (int i = 0; i < S; ++i) {
     const float ws = s_ws[warp][i];
     float o[8];
@@ -439,6 +442,7 @@ int composite_fwd_impl(const upnerf_composite_args* a, void* stream) {
   const CompArgs& p = *a;
   UPNERF_TRY(check_args(p, false));
   const unsigned grid = static_cast<unsigned>(ceil_div64(p.R, kWarps));
+  LaunchScope scope(kCatComposite, as_stream(stream));
   if (a->dtype == UPNERF_BF16)
     composite_fwd_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, as_stream(stream)>>>(p);
   else
@@ -451,6 +455,7 @@ int composite_bwd_impl(const upnerf_composite_args* a, void* stream) {
   const CompArgs& p = *a;
   UPNERF_TRY(check_args(p, true));
   const unsigned grid = static_cast<unsigned>(ceil_div64(p.R, kWarps));
+  LaunchScope scope(kCatComposite, as_stream(stream));
   if (a->dtype == UPNERF_BF16)
     composite_bwd_kernel<__nv_bfloat16><<<grid, kWarps * 32, 0, as_stream(stream)>>>(p);
   else

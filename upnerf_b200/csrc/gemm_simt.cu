@@ -142,6 +142,7 @@ extern "C" int upnerf_gemm_f32(const float* A, int64_t sam, int64_t sak, const f
   UPNERF_REQUIRE(mt < (1ll << 31) && nt < 65536 && split_k < 65536, UPNERF_ERR_BAD_SHAPE,
                  "gemm_f32: grid too large");
   dim3 grid(static_cast<unsigned>(mt), static_cast<unsigned>(nt), static_cast<unsigned>(split_k));
+  LaunchScope scope(kCatGemmSimt, as_stream(stream), 2.0 * M * N * K);
   gemm_simt_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
   UPNERF_CHECK_LAUNCH("gemm_simt_kernel");
   return UPNERF_OK;

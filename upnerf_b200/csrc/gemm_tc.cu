@@ -371,6 +371,7 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
     attr_set = true;
   }
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  LaunchScope scope(kCatGemmTc, as_stream(stream), 2.0 * M * N * K);
   gemm_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmA, tmB, tmC, tmAux, args);
   UPNERF_CHECK_LAUNCH("gemm_tc_kernel");
   return UPNERF_OK;

@@ -197,6 +197,7 @@ __global__ void pack_kernel(const PackList list) {
 int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, float* out, int64_t ld_out,
                 cudaStream_t st) {
   const int64_t n = R * dim;
+  LaunchScope scope(kCatHeads, st);
   gather_rows_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(table, idx, R, dim, out, ld_out);
   UPNERF_CHECK_LAUNCH("gather_rows_kernel");
   return UPNERF_OK;
@@ -205,6 +206,7 @@ int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, floa
 int scatter_add_rows(const float* src, int64_t ld_src, const int64_t* idx, int64_t R, int dim,
                      float* table, cudaStream_t st) {
   const int64_t n = R * dim;
+  LaunchScope scope(kCatHeads, st);
   scatter_add_rows_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(src, ld_src, idx, R, dim, table);
   UPNERF_CHECK_LAUNCH("scatter_add_rows_kernel");
   return UPNERF_OK;
@@ -212,6 +214,7 @@ int scatter_add_rows(const float* src, int64_t ld_src, const int64_t* idx, int64
 
 int ray_sum128(const void* X, int64_t ld, int64_t R, int S, float* out, int dtype, cudaStream_t st) {
   const unsigned grid = static_cast<unsigned>(ceil_div64(R, 4));
+  LaunchScope scope(kCatHeads, st);
   if (dtype == UPNERF_BF16)
     ray_sum128_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(X), ld, R, S, out);
   else
@@ -226,6 +229,7 @@ int rgb_head_bwd(const void* Q, int64_t ldq, const float* rgb, const float* d_rg
   int64_t blocks = ceil_div64(R, 8);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
   if (blocks > cap) blocks = cap;
+  LaunchScope scope(kCatHeads, st);
   if (dtype == UPNERF_BF16)
     rgb_head_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(Q), ldq, rgb, d_rgb, W2, R, S, static_cast<__nv_bfloat16*>(dQ),
@@ -247,6 +251,7 @@ int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N,
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  LaunchScope scope(kCatHeads, st);
   if (dtype == UPNERF_BF16)
     rowscale_colsum_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(X), ld, s, M, N, out, out_s);
@@ -259,6 +264,7 @@ int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N,
 
 int rowdot_head(const float* X, int64_t ld, int64_t M, int N, int nh, const float* w, const float* b,
                 int act, float* out, cudaStream_t st) {
+  LaunchScope scope(kCatHeads, st);
   rowdot_head_kernel<<<static_cast<unsigned>(ceil_div64(M, 4)), 128, 0, st>>>(X, ld, M, N, nh, w, b, act, out);
   UPNERF_CHECK_LAUNCH("rowdot_head_kernel");
   return UPNERF_OK;
@@ -267,6 +273,7 @@ int rowdot_head(const float* X, int64_t ld, int64_t M, int N, int nh, const floa
 int run_pack(const PackList& list, int dtype, cudaStream_t st) {
   if (list.n == 0) return UPNERF_OK;
   dim3 grid(64, list.n);
+  LaunchScope scope(kCatPack, st);
   if (dtype == UPNERF_BF16) pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(list);
   else pack_kernel<float><<<grid, 256, 0, st>>>(list);
   UPNERF_CHECK_LAUNCH("pack_kernel");

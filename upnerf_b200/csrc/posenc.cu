@@ -156,6 +156,7 @@ int upnerf_c2f_weights(const float* progress_dev, float start, float end, int us
   using namespace upnerf;
   UPNERF_REQUIRE(L >= 1 && L <= kMaxL, UPNERF_ERR_BAD_SHAPE, "c2f_weights: L=%d", L);
   UPNERF_REQUIRE(!use_c2f || progress_dev, UPNERF_ERR_BAD_SHAPE, "c2f_weights: progress missing");
+  LaunchScope scope(kCatPosenc, as_stream(stream));
   c2f_weights_kernel<<<1, 32, 0, as_stream(stream)>>>(progress_dev, start, end, use_c2f, L, band_w);
   UPNERF_CHECK_LAUNCH("c2f_weights_kernel");
   return UPNERF_OK;
@@ -168,6 +169,7 @@ int upnerf_posenc_fwd(const float* x, int64_t ld_x, int64_t M, int L, const floa
                  UPNERF_ERR_BAD_SHAPE, "posenc_fwd: M=%lld L=%d width=%d ld=%lld", (long long)M, L,
                  width, (long long)ld_out);
   const unsigned grid = static_cast<unsigned>(ceil_div64(M, 128));
+  LaunchScope scope(kCatPosenc, as_stream(stream));
   if (dtype == UPNERF_BF16)
     posenc_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
         x, ld_x, M, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out, width);
@@ -186,6 +188,7 @@ int upnerf_points_posenc_fwd(const float* rays, const float* z, int64_t n_rays, 
   UPNERF_REQUIRE(M > 0 && L >= 1 && L <= kMaxL && width >= 3 + 6 * L && ld_out >= width,
                  UPNERF_ERR_BAD_SHAPE, "points_posenc_fwd: bad sizes");
   const unsigned grid = static_cast<unsigned>(ceil_div64(M, 128));
+  LaunchScope scope(kCatPosenc, as_stream(stream));
   if (dtype == UPNERF_BF16)
     points_posenc_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
         rays, z, M, n_samples, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out, width);
@@ -203,6 +206,7 @@ int upnerf_points_posenc_bwd(const void* d_pe, int64_t ld_pe, const float* rays,
   UPNERF_REQUIRE(n_rays > 0 && n_samples > 0 && L >= 1 && L <= kMaxL, UPNERF_ERR_BAD_SHAPE,
                  "points_posenc_bwd: bad sizes");
   const unsigned grid = static_cast<unsigned>(ceil_div64(n_rays, 4));
+  LaunchScope scope(kCatPosenc, as_stream(stream));
   if (dtype == UPNERF_BF16)
     points_posenc_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(d_pe), ld_pe, rays, z, n_rays, n_samples, L, band_w, d_rays);

@@ -212,6 +212,7 @@ int upnerf_stratified_z(const float* rays, const float* perturb_rand, float pert
   UPNERF_REQUIRE(!(perturb > 0.f) || perturb_rand, UPNERF_ERR_BAD_SHAPE,
                  "stratified_z: perturb > 0 needs perturb_rand");
   const int64_t n = n_rays * n_samples;
+  LaunchScope scope(kCatSampling, as_stream(stream));
   stratified_z_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, as_stream(stream)>>>(
       rays, perturb_rand, perturb, use_disp, n_rays, n_samples, z);
   UPNERF_CHECK_LAUNCH("stratified_z_kernel");
@@ -225,6 +226,7 @@ int upnerf_sample_pdf(const float* bins, int64_t ld_bins, const float* weights, 
   UPNERF_REQUIRE(n_rays > 0 && n_importance > 0, UPNERF_ERR_BAD_SHAPE, "sample_pdf: bad sizes");
   UPNERF_REQUIRE(n_weights >= 1 && n_weights + 1 <= kMaxBins, UPNERF_ERR_BAD_SHAPE,
                  "sample_pdf: n_weights=%d unsupported (max %d)", n_weights, kMaxBins - 1);
+  LaunchScope scope(kCatSampling, as_stream(stream));
   sample_pdf_kernel<<<static_cast<unsigned>(ceil_div64(n_rays, kWarpsPerBlock)), kWarpsPerBlock * 32,
                       0, as_stream(stream)>>>(bins, ld_bins, weights, ld_weights, u, n_rays,
                                                n_weights, n_importance, eps, samples, inds, cdf_out);
@@ -237,6 +239,7 @@ int upnerf_searchsorted_right(const float* cdf, int n_cdf, const float* u, int n
   using namespace upnerf;
   UPNERF_REQUIRE(n_rays > 0 && n_cdf > 0 && n_u > 0, UPNERF_ERR_BAD_SHAPE, "searchsorted: bad sizes");
   const int64_t n = n_rays * n_u;
+  LaunchScope scope(kCatSampling, as_stream(stream));
   searchsorted_right_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, as_stream(stream)>>>(
       cdf, n_cdf, u, n_u, n_rays, inds);
   UPNERF_CHECK_LAUNCH("searchsorted_right_kernel");
@@ -251,6 +254,7 @@ int upnerf_resample_merge(const float* z, const float* w0, const float* w1, int6
   UPNERF_REQUIRE(n_samples - 1 <= kMaxBins && n_samples + n0 + n1 <= kMaxFine, UPNERF_ERR_BAD_SHAPE,
                  "resample_merge: S=%d n0=%d n1=%d exceeds limits", n_samples, n0, n1);
   ResampleArgs a{z, w0, w1, ld_w, u0, u1, n0, n1, n_rays, n_samples, eps, z_fine};
+  LaunchScope scope(kCatSampling, as_stream(stream));
   resample_merge_kernel<<<static_cast<unsigned>(ceil_div64(n_rays, kWarpsPerBlock)),
                           kWarpsPerBlock * 32, 0, as_stream(stream)>>>(a);
   UPNERF_CHECK_LAUNCH("resample_merge_kernel");

@@ -79,6 +79,7 @@ def net_config(model) -> L.NetConfig:
 
 def flat_parameters(model) -> torch.Tensor:
     """All parameters as ONE fp32 vector in state_dict order (autograd splits the gradient back)."""
-    ps = [p.reshape(-1) for p in model.parameters()]
-    flat = torch.cat(ps)
-    return flat
+    getter = getattr(model, "_upnerf_flat", None)
+    if getter is not None:      # parameters already live in one flat buffer (NeRFSystem.model_setup)
+        return getter()
+    return torch.cat([p.reshape(-1) for p in model.parameters()])

@@ -1,0 +1,285 @@
+"""`NeRFSystem` -- the train-step driver with the reference's method names and hparams keys
+(models/nerf_system.py:22-461), re-hosted on the CUDA path.
+
+It is a plain `nn.Module` (pytorch-lightning is not a dependency here); `forward`,
+`training_step`, `model_setup`, `configure_optimizers` and `get_schedule_mult` keep the
+reference's signatures so a Lightning subclass can mix it in unchanged.  Differences that are
+deliberate and invisible to results:
+  * every trainable tensor is a VIEW into one of two flat fp32 buffers (networks+embeddings /
+    pose+depth-scale), with gradients in matching flat buffers -- the CUDA kernels accumulate
+    straight into them, one fused Adam updates each, and data-parallel training needs exactly
+    one all-reduce per buffer per step (the reference's DDP buckets, train.py:72);
+  * `progress` is mirrored on the host, so there is no per-step `.item()` sync
+    (models/nerf_system.py:180);
+  * pose refinement + ray casting is one fused kernel (`refine_rays`).
+"""
+from __future__ import annotations
+
+import math
+from collections import defaultdict
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from ..losses import UPNeRFLoss
+from ..utils import ray as ray_utils
+from .nerf import NeRF
+from .rendering import render_rays
+from .transient_net import TransientNet
+
+
+def default_hparams() -> dict:
+    """The reference's shipped defaults (configs/default.yaml + configs/brandenburg_gate.yaml), flat
+    dotted keys like configs/config.py produces."""
+    return {
+        "seed": 42, "num_gpus": 1, "debug": False,
+        "nerf.N_samples": 128, "nerf.N_importance": 128, "nerf.N_emb_xyz": 10, "nerf.N_emb_dir": 4,
+        "nerf.near": 0.1, "nerf.far": 5.0, "nerf.appearance_dim": 48, "nerf.candidate_dim": 16,
+        "nerf.feat_dim": 384, "nerf.use_disp": False, "nerf.perturb": 1.0,
+        "t_net.beta_min": 0.1, "t_net.transient_dim": 128, "t_net.feat_dim": 384,
+        "loss.depth_mult": 1e-3, "loss.alpha_reg": 1.0,
+        "optimizer.type": "adam", "optimizer.lr": 5e-4, "optimizer.scheduler.type": "ExponentialLR",
+        "optimizer.scheduler.lr_end": 5e-5,
+        "optimizer_pose.type": "adam", "optimizer_pose.lr": 2e-3,
+        "optimizer_pose.scheduler.type": "ExponentialLR", "optimizer_pose.scheduler.lr_end": 1e-5,
+        "max_steps": 600000, "train.batch_size": 2048, "train.log_pose_interval": 3000,
+        "val.chunk_size": 4096,
+        "pose.optimize": True, "pose.c2f": (0.1, 0.5), "pose.noise": -1,
+        "candidate_schedule": (0.1, 0.5),
+        "kernel.precision": "bf16",
+    }
+
+
+class FlatGroup:
+    """Parameters re-homed as views of one flat fp32 buffer, gradients likewise."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        n = sum(p.numel() for p in self.params)
+        self.flat = nn.Parameter(torch.empty(n, device=device, dtype=torch.float32))
+        self.flat.grad = torch.zeros(n, device=device, dtype=torch.float32)
+        off = 0
+        self.offsets = {}
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat.data[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat.data[off:off + k].view(p.shape)
+                p.grad = self.flat.grad[off:off + k].view(p.shape)
+                self.offsets[id(p)] = (off, k)
+                off += k
+
+    def zero_grad(self):
+        self.flat.grad.zero_()
+
+    def slice_of(self, params):
+        """Getter of the autograd-visible slice of the flat leaf covering a run of consecutive parameters."""
+        params = list(params)
+        a = self.offsets[id(params[0])][0]
+        o, k = self.offsets[id(params[-1])]
+        return lambda: self.flat[a:o + k]
+
+
+def allreduce_mean_(t: torch.Tensor) -> None:
+    """DDP gradient semantics (train.py:72): mean over ranks, one collective per flat buffer."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    if t.is_cuda:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(dist.get_world_size())
+
+
+class NeRFSystem(nn.Module):
+    def __init__(self, hparams, N_images_train=None, device="cuda"):
+        super().__init__()
+        self.hparams = dict(default_hparams(), **dict(hparams))
+        self.candidate_schedule = self.hparams["candidate_schedule"]
+        self.fine = self.hparams["nerf.N_importance"] > 0
+        self.loss = UPNeRFLoss(depth_mult=self.hparams["loss.depth_mult"], alpha_reg=self.hparams["loss.alpha_reg"],
+                               encode_feat=self.hparams["nerf.feat_dim"] > 0, fine=self.fine)
+        self.global_step = 0
+        self.logged = {}
+        self._device = torch.device(device)
+        self._progress = 0.0
+        self.white_back = False
+        if N_images_train is not None:
+            self.model_setup(N_images_train)
+            self.configure_optimizers()
+
+    # ------------------------------------------------------------------ construction
+    def model_setup(self, N_images=None):
+        """models/nerf_system.py:340-409 (same attribute names and state_dict keys)."""
+        hp = self.hparams
+        if N_images is None:
+            N_images = self.train_dataset.N_images_train
+        self.N_images = N_images
+        self.embeddings = {}
+        for which in ("coarse", "fine") if self.fine else ("coarse",):
+            for tag, dim in (("a", hp["nerf.appearance_dim"]), ("c", hp["nerf.candidate_dim"])):
+                if dim > 0:
+                    e = nn.Embedding(N_images, dim)
+                    setattr(self, f"embedding_{which}_{tag}", e)
+                    self.embeddings[f"{which}_{tag}"] = e
+        mk = lambda typ: NeRF(typ, encode_feat=hp["nerf.feat_dim"] > 0, feat_dim=hp["nerf.feat_dim"],
+                              xyz_L=hp["nerf.N_emb_xyz"], dir_L=hp["nerf.N_emb_dir"],
+                              appearance_dim=hp["nerf.appearance_dim"], candidate_dim=hp["nerf.candidate_dim"],
+                              c2f=hp["pose.c2f"])
+        self.nerf_coarse = mk("coarse")
+        self.models = {"nerf_coarse": self.nerf_coarse}
+        if self.fine:
+            self.nerf_fine = mk("fine")
+            self.models["nerf_fine"] = self.nerf_fine
+        self.transient_net = TransientNet(N_images=N_images, beta_min=hp["t_net.beta_min"],
+                                          trasient_dim=hp["t_net.transient_dim"], feat_dim=hp["t_net.feat_dim"])
+        self.models["transient_network"] = self.transient_net
+        self.se3_refine = nn.Embedding(N_images, 6)
+        nn.init.zeros_(self.se3_refine.weight)
+        self.depth_scale = nn.Embedding(N_images, 2)
+        nn.init.zeros_(self.depth_scale.weight)
+        self.to(self._device)
+        # flat buffers: group 0 = reference optimizer 0 (networks + embeddings), group 1 = pose
+        main = []
+        for m in self.models.values():
+            main += list(m.parameters())
+        for e in self.embeddings.values():
+            main += list(e.parameters())
+        self.group_main = FlatGroup(main, self._device)
+        self.group_pose = FlatGroup([self.depth_scale.weight, self.se3_refine.weight], self._device)
+        for m in (self.nerf_coarse, *( [self.nerf_fine] if self.fine else [])):
+            m._upnerf_flat = self.group_main.slice_of(m.parameters())
+
+    def load_state_dict(self, sd, strict=True):
+        # parameters are views of the flat buffers: copy in place so the views stay valid
+        own = self.state_dict()
+        missing = [k for k in own if k not in sd]
+        unexpected = [k for k in sd if k not in own]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"state_dict mismatch: missing {missing[:5]} unexpected {unexpected[:5]}")
+        with torch.no_grad():
+            for k, v in sd.items():
+                if k in own:
+                    own[k].copy_(v)
+        self._progress = float(self.nerf_coarse.progress.data.item())
+
+    def configure_optimizers(self):
+        """Two Adam(eps=1e-8) + ExponentialLR pairs (models/nerf_system.py:41-73, utils/optim.py:20-44)."""
+        hp = self.hparams
+        fused = self._device.type == "cuda"
+
+        def make(prefix, flat):
+            if hp[f"{prefix}.type"] != "adam":
+                raise NotImplementedError(hp[f"{prefix}.type"])
+            opt = torch.optim.Adam([flat], lr=hp[f"{prefix}.lr"], eps=1e-8, fused=fused)
+            gamma = (hp[f"{prefix}.scheduler.lr_end"] / hp[f"{prefix}.lr"]) ** (1.0 / hp["max_steps"])
+            return opt, torch.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma)
+
+        self.optimizer, self.scheduler = make("optimizer", self.group_main.flat)
+        self._optimizers, self._schedulers = [self.optimizer], [self.scheduler]
+        if hp["pose.optimize"]:
+            self.optimizer_pose, self.scheduler_pose = make("optimizer_pose", self.group_pose.flat)
+            self._optimizers.append(self.optimizer_pose)
+            self._schedulers.append(self.scheduler_pose)
+        return self._optimizers, self._schedulers
+
+    def optimizers(self):
+        return self._optimizers
+
+    def lr_schedulers(self):
+        return self._schedulers
+
+    def log(self, key, value, **kw):
+        self.logged[key] = value
+
+    # ------------------------------------------------------------------ schedule
+    def get_schedule_mult(self, progress):
+        """models/nerf_system.py:452-461."""
+        s, e = self.candidate_schedule
+        if progress < s:
+            return 0
+        if progress > e:
+            return 1
+        return (1 - math.cos(math.pi * (progress - s) / (e - s))) / 2
+
+    def set_progress(self, progress: float):
+        self._progress = float(progress)
+        self.nerf_coarse.progress.data.fill_(self._progress)
+        if self.fine:
+            self.nerf_fine.progress.data.fill_(self._progress)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, rays, feats, img_idx, sched_mult, train=True, rng=None):
+        """Chunked render + transient blend (models/nerf_system.py:93-148)."""
+        hp = self.hparams
+        B = rays.shape[0]
+        chunk = B if train else hp["val.chunk_size"]
+        results = defaultdict(list)
+        for i in range(0, B, chunk):
+            part = render_rays(models=self.models, embeddings=self.embeddings, rays=rays[i:i + chunk],
+                               img_idx=img_idx[i:i + chunk], sched_mult=sched_mult,
+                               sched_phase=0 if sched_mult == 0 else (2 if sched_mult == 1 else 1),
+                               N_samples=hp["nerf.N_samples"], use_disp=hp["nerf.use_disp"],
+                               perturb=hp["nerf.perturb"] if train else 0, N_importance=hp["nerf.N_importance"],
+                               white_back=self.white_back, encode_feat=hp["nerf.feat_dim"] > 0,
+                               validation=not train, precision=hp["kernel.precision"], rng=rng)
+            for k, v in part.items():
+                results[k].append(v)
+        results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
+        if sched_mult > 0:
+            t = self.transient_net(feats, img_idx)
+            a, c = t["alpha"], t["rgb"]
+            results["rgb_coarse"] = results["s_rgb_coarse"] * (1 - a.detach()) + c.detach() * a.detach()
+            if self.fine:
+                results["rgb_fine"] = results["s_rgb_fine"] * (1 - a) + c * a
+            results["t_beta"], results["t_alpha"] = t["beta"], a
+        return results
+
+    # ------------------------------------------------------------------ one optimisation step
+    def training_step(self, batch, batch_nb=0, rng=None):
+        """models/nerf_system.py:150-229."""
+        hp = self.hparams
+        img_idx = batch["img_idx"]
+        if hp["pose.optimize"]:
+            rays = ray_utils.refine_rays(self.se3_refine.weight, img_idx, batch["c2w"], batch["directions"],
+                                         batch["ray_infos"])
+        else:
+            o, d = ray_utils.get_rays(batch["directions"], batch["c2w"])
+            rays = torch.cat([o, d, batch["ray_infos"]], 1)
+        # monocular-depth affine correction (:169-177)
+        scale, shift = torch.unbind(self.depth_scale(img_idx), 1)
+        inv = batch["inv_depths"] * torch.exp(scale) + shift
+        inv = torch.where(inv < 1 / hp["nerf.far"], torch.full_like(inv, 1 / hp["nerf.far"]), inv)
+        depth = 1.0 / inv
+        depth = torch.where(depth < hp["nerf.near"], torch.full_like(depth, hp["nerf.near"]), depth)
+
+        sched_mult = self.get_schedule_mult(self._progress)
+        results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng)
+        loss_d = self.loss(results, batch["rgbs"], batch["feats"], depth, sched_mult)
+        loss = sum(loss_d.values())
+
+        self.group_main.zero_grad()
+        self.group_pose.zero_grad()
+        loss.backward()
+        allreduce_mean_(self.group_main.flat.grad)
+        if hp["pose.optimize"]:
+            allreduce_mean_(self.group_pose.flat.grad)
+        for opt, sch in zip(self._optimizers, self._schedulers):
+            opt.step()
+            sch.step()
+
+        with torch.no_grad():
+            typ = "fine" if self.fine else "coarse"
+            if f"s_rgb_{typ}" in results:
+                psnr_ = -10 * torch.log10(((results[f"s_rgb_{typ}"] - batch["rgbs"]) ** 2).mean())
+            else:
+                psnr_ = torch.zeros(1)
+        self.log("train/loss", loss.detach())
+        for k, v in loss_d.items():
+            self.log(f"train/{k}", v.detach())
+        self.log("train/psnr", psnr_)
+        self.global_step += len(self._optimizers)
+        if hp["pose.optimize"]:
+            self.set_progress(self.global_step / (hp["max_steps"] * 2))
+        return loss
