@@ -51,18 +51,23 @@ def test_training_step_matches_oracle_fp32(cuda_dev, start_progress):
         l = sys_.training_step(bd, it, rng=rng)
         assert abs(float(l) - float(l_ref)) <= 1e-4 * max(1.0, abs(float(l_ref))), (it, float(l), float(l_ref))
     # parameters after two Adam steps
+    # Adam's first steps are ~lr*sign(g): an element whose gradient is at rounding-noise level may
+    # legitimately take the opposite +-lr step, so updates are compared norm-wise per tensor.
     own = sys_.state_dict()
     worst = 0.0
     for k, v in orc.p.items():
         if k.endswith("progress"):
             continue
-        diff = float((own[k].cpu() - v.detach()).abs().max())
-        # Adam's first steps move each weight by ~lr regardless of gradient scale: compare to lr
-        lr = 2e-3 if k.startswith(("se3_refine", "depth_scale")) else 5e-4
-        worst = max(worst, diff / lr)
-        assert diff <= 0.05 * lr * 2 + 1e-7, (k, diff)
+        upd_ref = v.detach() - sd[k]
+        upd = own[k].cpu() - sd[k]
+        if float(upd_ref.abs().max()) == 0:
+            assert float(upd.abs().max()) == 0, k
+            continue
+        r = float((upd - upd_ref).norm() / upd_ref.norm())
+        worst = max(worst, r)
+        assert r <= 0.1, (k, r)
     assert abs(sys_._progress - orc.progress) < 1e-9
-    print(f"worst parameter deviation after 2 steps: {worst:.3f} x lr")
+    print(f"worst relative update error after 2 Adam steps: {worst:.3e}")
 
 
 def test_psnr_parity_after_fixed_steps(cuda_dev):

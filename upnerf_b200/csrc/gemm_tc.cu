@@ -5,15 +5,19 @@
 // Replaces the nn.Linear (+activation) calls of NeRF.forward (reference models/nerf.py:84-123)
 // and, with transposed weights, their data-gradient in backward.
 //
-// Structure (one persistent CTA per SM, 6 warps, warp-specialised):
-//   warp 0      TMA producer: A tile 128x64 and B tile Nx64 per stage, 128-byte swizzle
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x N x 16)
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (thread = output row), fused
-//               bias / per-ray bias / rank-1 / aux-add / ReLU / ReLU-mask / row-dot heads,
-//               bf16 pack into a swizzled smem box, TMA store
-// Two 256-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs
-// of tile i+1.  The aux operand (residual or ReLU mask) is TMA-loaded into the very smem
-// box the result is later stored from, two boxes ahead of its use.
+// Structure (one persistent CTA per SM, 18 warps, warp-specialised):
+//   warp 0       TMA producer: A tile 128x64 and B tile Nx64 per stage, 128-byte swizzle
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x N x 16)
+//   warps 2..17  epilogue, four groups of four warps (a group covers the four TMEM lane
+//                quadrants; thread = output row).  Output boxes of 128 rows x 64 columns are
+//                dealt round-robin to the groups; each group tcgen05.ld's its box, applies
+//                bias / per-ray bias / rank-1 / aux-add / ReLU / ReLU-mask / row-dot heads,
+//                packs bf16 into its swizzled smem box and TMA-stores it.
+// Two 256-column TMEM accumulators ping-pong so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  The epilogue is the instruction-bound part of a 256-wide layer (one warp per
+// SM sub-partition cannot hide its own latencies), hence four warps per sub-partition.
+// The aux operand (residual or ReLU mask) is TMA-loaded into the very smem box the result
+// is later stored from, one box ahead of its use.
 #include <cuda_bf16.h>
 #include <string.h>
 
@@ -31,21 +35,24 @@ constexpr int kBK = 64;           // K elements per stage = one 128-byte swizzle
 constexpr int kABytes = kBM * 128;
 constexpr int kBBytesMax = 256 * 128;
 constexpr int kCBytes = kBM * 128;  // one 128 x 64 bf16 output box
-constexpr int kNumCBuf = 4;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kGroups = 4;          // epilogue warp groups (one C box each)
+constexpr int kEpiThreads = kGroups * 128;
+constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kMaxN = 256;
 constexpr int kMaxHeads = 3;
 
 constexpr int kOffA = 0;
 constexpr int kOffB = kOffA + kStages * kABytes;
 constexpr int kOffC = kOffB + kStages * kBBytesMax;
-constexpr int kOffVec = kOffC + kNumCBuf * kCBytes;
+constexpr int kOffVec = kOffC + kGroups * kCBytes;
 constexpr int kVecFloats = kMaxN * (2 + kMaxHeads);
-constexpr int kOffBar = kOffVec + kVecFloats * 4;
-constexpr int kNumBars = 2 * kStages + 4 + kNumCBuf;
+constexpr int kOffHead = kOffVec + kVecFloats * 4;
+constexpr int kHeadFloats = 2 * kGroups * kBM * kMaxHeads;   // [acc][group][row][head]
+constexpr int kOffBar = kOffHead + kHeadFloats * 4;
+constexpr int kNumBars = 2 * kStages + 4 + kGroups;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + slack for manual 1024-byte alignment
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
 struct GemmArgs {
   int64_t M;
@@ -72,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + kOffB;
   uint8_t* sC = smem + kOffC;
   float* sVec = reinterpret_cast<float*>(smem + kOffVec);
+  float* sHead = reinterpret_cast<float*>(smem + kOffHead);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + kStages;
@@ -100,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&bar_tfull[i], 1);
       mbar_init(&bar_tempty[i], kEpiThreads);
     }
-    for (int i = 0; i < kNumCBuf; ++i) mbar_init(&bar_aux[i], 1);
+    for (int i = 0; i < kGroups; ++i) mbar_init(&bar_aux[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_holder);
@@ -172,32 +180,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int row_in_tile = quad * 32 + lane;
-    const bool leader = (threadIdx.x == 64);
+    const bool leader = ((ew & 3) == 0) && lane == 0;
+    const uint32_t bar_id = 1 + grp;  // named barrier of this group (128 threads)
     const upnerf_epilogue& ep = args.ep;
     const int nh = ep.n_heads;
-    int t = 0;
-    uint32_t q = 0;  // running output-box index of this CTA (selects the smem box)
+    uint8_t* cbuf = sC + grp * kCBytes;
+    uint8_t* crow_ptr = cbuf + row_in_tile * 128;
+    uint64_t* my_aux = &bar_aux[grp];
 
-    // total boxes this CTA will process, for the aux prefetch
     int my_tiles = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
-    const uint32_t total_boxes = static_cast<uint32_t>(my_tiles) * nchunks;
-    auto issue_aux = [&](uint32_t box) {
-      // box -> (tile, chunk)
+    const int total_boxes = my_tiles * nchunks;
+    // first box of this group at or after box index b0 (box = local_tile * nchunks + chunk)
+    auto next_box = [&](int b0) -> int {
+      const int b = b0 + ((grp - b0) & (kGroups - 1));
+      return b < total_boxes ? b : -1;
+    };
+    auto issue_aux = [&](int box) {
       const int lt = box / nchunks;
-      const int ch = box % nchunks;
+      const int ch = box - lt * nchunks;
       const int tile = blockIdx.x + lt * gridDim.x;
-      uint64_t* b = &bar_aux[box % kNumCBuf];
-      mbar_arrive_expect_tx(b, kCBytes);
-      tma_load_2d(sC + (box % kNumCBuf) * kCBytes, &tmAux, b, ch * 64, tile * kBM);
+      mbar_arrive_expect_tx(my_aux, kCBytes);
+      tma_load_2d(cbuf, &tmAux, my_aux, ch * 64, tile * kBM);
     };
     if (has_aux && leader) {
-      if (total_boxes > 0) issue_aux(0);
-      if (total_boxes > 1) issue_aux(1);
+      const int b = next_box(0);
+      if (b >= 0) issue_aux(b);
     }
+    uint32_t qg = 0;  // boxes this group has processed (aux barrier phase)
 
+    int t = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const int64_t grow = static_cast<int64_t>(tile) * kBM + row_in_tile;
@@ -207,111 +223,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* rb = ep.ray_bias ? ep.ray_bias + (crow / ep.rows_per_ray) * N : nullptr;
       float hacc[kMaxHeads] = {0.f, 0.f, 0.f};
 
+      // chunks of this tile owned by this group: first, first + 4, ...
+      const int first = (grp - t * nchunks) & (kGroups - 1);
+      int last = -1;
+      for (int ch = first; ch < nchunks; ch += kGroups) last = ch;
+
       mbar_wait(&bar_tfull[acc], (t >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256;
+      if (last < 0) {
+        tc_fence_before_sync();
+        mbar_arrive(&bar_tempty[acc]);
+      }
 
-      for (int ch = 0; ch < nchunks; ++ch, ++q) {
-        const uint32_t buf = q % kNumCBuf;
-        uint8_t* cbuf = sC + buf * kCBytes;
-        // The box last used this smem buffer kNumCBuf boxes ago; its TMA store must have
-        // finished reading.  The leader keeps at most one store in flight before this point.
-        if (leader) {
-          tma_store_wait_read<1>();
-          if (has_aux && q + 2 < total_boxes) issue_aux(q + 2);
-        }
+      for (int ch = first; ch < nchunks; ch += kGroups) {
+        // the smem box is free once the previous store of this group has been read out (the
+        // leader waited for that before issuing the aux load / arriving at the barrier)
         if (has_aux) {
-          mbar_wait(&bar_aux[buf], (q / kNumCBuf) & 1);
+          mbar_wait(my_aux, qg & 1);
         } else {
-          named_bar_sync(1, kEpiThreads);
+          named_bar_sync(bar_id, 128);
         }
-
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(taddr + ch * 64, v0);
-        tmem_ld_32x32(taddr + ch * 64 + 32, v1);
-        tmem_ld_wait();
-        if (ch == nchunks - 1) {
-          // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before_sync();
-          mbar_arrive(&bar_tempty[acc]);
-        }
-
-        uint8_t* crow_ptr = cbuf + row_in_tile * 128;
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float v[8];
+        for (int half = 0; half < 2; ++half) {
+          uint32_t acc_r[32];
+          tmem_ld_32x32(taddr + ch * 64 + half * 32, acc_r);
+          tmem_ld_wait();
+          if (half == 1 && ch == last) {
+            // accumulator fully read by this thread: hand it back to the MMA warp
+            tc_fence_before_sync();
+            mbar_arrive(&bar_tempty[acc]);
+          }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int i = c8 * 8 + e;
-            v[e] = __uint_as_float(i < 32 ? v0[i] : v1[i - 32]);
-          }
-          const int col = ch * 64 + c8 * 8;
-          const float4 b0 = *reinterpret_cast<const float4*>(&sVec[col]);
-          const float4 b1 = *reinterpret_cast<const float4*>(&sVec[col + 4]);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          if (rb) {
-            const float4 p0 = __ldg(reinterpret_cast<const float4*>(rb + col));
-            const float4 p1 = __ldg(reinterpret_cast<const float4*>(rb + col + 4));
-            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-          }
-          if (ep.rank1_row) {
-            const float4 c0 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col]);
-            const float4 c1 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col + 4]);
-            v[0] += r1 * c0.x; v[1] += r1 * c0.y; v[2] += r1 * c0.z; v[3] += r1 * c0.w;
-            v[4] += r1 * c1.x; v[5] += r1 * c1.y; v[6] += r1 * c1.z; v[7] += r1 * c1.w;
-          }
-          uint4* slot = reinterpret_cast<uint4*>(crow_ptr + ((c8 ^ (row_in_tile & 7)) << 4));
-          float a[8];
-          if (has_aux) {
-            const uint4 au = *slot;
-            const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&au);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int c8 = half * 4 + c4;
+            float v[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(ab[e]);
-              a[2 * e] = f.x;
-              a[2 * e + 1] = f.y;
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc_r[c4 * 8 + e]);
+            const int col = ch * 64 + c8 * 8;
+            const float4 b0 = *reinterpret_cast<const float4*>(&sVec[col]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sVec[col + 4]);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if (rb) {
+              const float4 p0 = __ldg(reinterpret_cast<const float4*>(rb + col));
+              const float4 p1 = __ldg(reinterpret_cast<const float4*>(rb + col + 4));
+              v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+              v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
             }
-            if (ep.aux_mode == 1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += a[e];
+            if (ep.rank1_row) {
+              const float4 c0 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col]);
+              const float4 c1 = *reinterpret_cast<const float4*>(&sVec[kMaxN + col + 4]);
+              v[0] += r1 * c0.x; v[1] += r1 * c0.y; v[2] += r1 * c0.z; v[3] += r1 * c0.w;
+              v[4] += r1 * c1.x; v[5] += r1 * c1.y; v[6] += r1 * c1.z; v[7] += r1 * c1.w;
             }
-          }
-          if (ep.act == 1) {
+            uint4* slot = reinterpret_cast<uint4*>(crow_ptr + ((c8 ^ (row_in_tile & 7)) << 4));
+            float a[8];
+            if (has_aux) {
+              const uint4 au = *slot;
+              const __nv_bfloat162* ab = reinterpret_cast<const __nv_bfloat162*>(&au);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (ep.aux_mode == 2) {
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(ab[e]);
+                a[2 * e] = f.x;
+                a[2 * e + 1] = f.y;
+              }
+              if (ep.aux_mode == 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
-          }
-          for (int h = 0; h < nh; ++h) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
-            hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
-                       v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
-          }
-          uint4 out;
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&out);
+                for (int e = 0; e < 8; ++e) v[e] += a[e];
+              }
+            }
+            if (ep.act == 1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          *slot = out;
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (ep.aux_mode == 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
+            }
+            for (int h = 0; h < nh; ++h) {
+              const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
+              hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
+                         v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+            }
+            uint4 out;
+            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            *slot = out;
+          }
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
+        named_bar_sync(bar_id, 128);
         if (leader) {
           tma_store_2d(&tmC, cbuf, ch * 64, tile * kBM);
           tma_store_commit();
+          tma_store_wait_read<0>();  // box reusable; overlaps the other groups' work
+          if (has_aux) {
+            const int nb = next_box(t * nchunks + ch + 1);
+            if (nb >= 0) issue_aux(nb);
+          }
         }
+        ++qg;
       }
 
-      if (nh > 0 && row_ok) {
-        for (int h = 0; h < nh; ++h) {
-          float x = hacc[h] + ep.head_b[h];
-          if (ep.head_act == 1) x = softplus_ref(x);
-          else if (ep.head_act == 2) x = sigmoid_ref(x);
-          ep.head_out[grow * nh + h] = x;
+      if (nh > 0) {
+        // row-dot heads: partial sums of the groups are combined by group 0
+        float* slot = sHead + ((acc * kGroups + grp) * kBM + row_in_tile) * kMaxHeads;
+        for (int h = 0; h < nh; ++h) slot[h] = hacc[h];
+        named_bar_sync(6, kEpiThreads);
+        if (grp == 0 && row_ok) {
+          for (int h = 0; h < nh; ++h) {
+            float x = ep.head_b[h];
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g)
+              x += sHead[((acc * kGroups + g) * kBM + row_in_tile) * kMaxHeads + h];
+            if (ep.head_act == 1) x = softplus_ref(x);
+            else if (ep.head_act == 2) x = sigmoid_ref(x);
+            ep.head_out[grow * nh + h] = x;
+          }
         }
       }
     }
@@ -344,7 +375,7 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   args.N = N;
   args.K = K;
   const int64_t tiles = ceil_div64(M, kBM);
-  UPNERF_REQUIRE(tiles < (1ll << 30), UPNERF_ERR_BAD_SHAPE, "gemm_bf16: M too large");
+  UPNERF_REQUIRE(tiles < (1ll << 28), UPNERF_ERR_BAD_SHAPE, "gemm_bf16: M too large");
   args.num_tiles = static_cast<int>(tiles);
   if (ep) args.ep = *ep;
   UPNERF_REQUIRE(args.ep.n_heads >= 0 && args.ep.n_heads <= kMaxHeads, UPNERF_ERR_BAD_SHAPE,
