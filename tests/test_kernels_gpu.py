@@ -185,7 +185,7 @@ def test_sample_pdf_golden(cuda_dev):
         # against the reference's own output: (u - cdf)/denom amplifies the 1-ulp CDF difference in
         # near-empty bins (denom ~ 1e-5), so the bound scales with the conditioning of the bin
         err = (out.cpu() - g[s_key]).abs()
-        bound = 2e-5 + 1e-6 * (b1 - b0).abs() / den
+        bound = 2e-5 + 2e-6 * (b1 - b0).abs() / den
         assert (err <= bound).all(), float((err - bound).max())
         if i_key:
             assert (inds.cpu() != g[i_key]).float().mean() < 0.02

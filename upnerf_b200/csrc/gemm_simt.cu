@@ -13,7 +13,7 @@
 namespace upnerf {
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 32;
 
 struct SimtArgs {
   const float* A;
@@ -32,8 +32,9 @@ struct SimtArgs {
 
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const SimtArgs a) {
-  __shared__ float As[TK][TM + 4];
-  __shared__ float Bs[TK][TN + 4];
+  // double-buffered tiles: the global loads of tile i+1 are in flight while tile i is consumed
+  __shared__ float As[2][TK][TM + 4];
+  __shared__ float Bs[2][TK][TN + 4];
   const int tid = threadIdx.x;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * TM;
   const int64_t n0 = static_cast<int64_t>(blockIdx.y) * TN;
@@ -51,34 +52,60 @@ gemm_simt_kernel(const SimtArgs a) {
 
   const bool a_kfast = (a.sak == 1);
   const bool b_kfast = (a.sbk == 1);
+  constexpr int kPerThread = TM * TK / 256;
+  float ra[kPerThread], rb[kPerThread];
 
-  for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
+  auto load_tile = [&](int64_t k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPerThread; ++i) {
       const int e = tid + i * 256;
       int kk, mm;
-      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
       const int64_t gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < a.M && gk < kend) ? a.A[gm * a.sam + gk * a.sak] : 0.f;
+      ra[i] = (gm < a.M && gk < kend) ? __ldg(a.A + gm * a.sam + gk * a.sak) : 0.f;
       int kb, nn;
-      if (b_kfast) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
+      if (b_kfast) { kb = e % TK; nn = e / TK; } else { nn = e % TN; kb = e / TN; }
       const int64_t gn = n0 + nn, gk2 = k0 + kb;
-      Bs[kb][nn] = (gn < a.N && gk2 < kend) ? a.B[gn * a.sbn + gk2 * a.sbk] : 0.f;
+      rb[i] = (gn < a.N && gk2 < kend) ? __ldg(a.B + gn * a.sbn + gk2 * a.sbk) : 0.f;
     }
-    __syncthreads();
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+      const int e = tid + i * 256;
+      int kk, mm;
+      if (a_kfast) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      As[buf][kk][mm] = ra[i];
+      int kb, nn;
+      if (b_kfast) { kb = e % TK; nn = e / TK; } else { nn = e % TN; kb = e / TN; }
+      Bs[buf][kb][nn] = rb[i];
+    }
+  };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    load_tile(kbeg);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
+    const bool more = k0 + TK < kend;
+    if (more) load_tile(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float av[4], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) av[i] = As[buf][kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[buf][kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (more) store_tile(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 
   const upnerf_epilogue& ep = a.ep;

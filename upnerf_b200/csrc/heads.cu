@@ -170,7 +170,7 @@ rowdot_head_kernel(const float* __restrict__ X, int64_t ld, int64_t M, int N, in
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
-      float x = acc + b[h];
+      float x = acc + (b ? b[h] : 0.f);
       if (act == 1) x = softplus_ref(x);
       else if (act == 2) x = sigmoid_ref(x);
       out[m * nh + h] = x;
@@ -244,6 +244,15 @@ int rgb_head_bwd(const void* Q, int64_t ldq, const float* rgb, const float* d_rg
 
 int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N, float* out,
                     float* out_s, int dtype, cudaStream_t st) {
+  // wide inputs are processed in column tiles of 128
+  if (N > 256) {
+    UPNERF_REQUIRE(N % 128 == 0, UPNERF_ERR_BAD_SHAPE, "rowscale_colsum: N=%d", N);
+    const size_t es = dtype == UPNERF_BF16 ? 2 : 4;
+    for (int c = 0; c < N; c += 128)
+      UPNERF_TRY(rowscale_colsum(static_cast<const uint8_t*>(X) + c * es, ld, s, M, 128, out + c,
+                                 c == 0 ? out_s : nullptr, dtype, st));
+    return UPNERF_OK;
+  }
   UPNERF_REQUIRE(N >= 2 && N <= 256 && N % 2 == 0 && 256 % (N / 2) == 0, UPNERF_ERR_BAD_SHAPE,
                  "rowscale_colsum: N=%d", N);
   const int groups = 256 / (N / 2);

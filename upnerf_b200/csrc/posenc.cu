@@ -93,6 +93,49 @@ __global__ void points_posenc_fwd_kernel(const float* __restrict__ rays, const f
   encode_row<T>(v, L, bw, out + m * ld_row, width);
 }
 
+
+// Tiled variant for width == 64 (the xyz encoding feeding layer 1 / the skip buffer): each thread
+// encodes one row into shared memory, then the block writes the 128 rows with 16-byte stores
+// (a warp covers four 128-byte rows per instruction instead of 32 scattered 2-byte stores).
+template <typename T>
+__global__ void __launch_bounds__(128)
+points_posenc_fwd_tiled_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t M, int S,
+                               int L, const float* __restrict__ band_w, T* __restrict__ out, int64_t ld_row) {
+  __shared__ float bw[kMaxL];
+  __shared__ float tile[128][65];
+  if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
+  __syncthreads();
+  const int64_t m0 = blockIdx.x * 128ll;
+  const int64_t m = m0 + threadIdx.x;
+  if (m < M) {
+    const int64_t r = m / S;
+    const float* ray = rays + r * 8;
+    const float zz = z[m];
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
+    encode_row<float>(v, L, bw, &tile[threadIdx.x][0], 64);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 128 * 8; idx += 128) {
+    const int row = idx >> 3, c8 = idx & 7;
+    if (m0 + row >= M) continue;
+    const float* src = &tile[row][c8 * 8];
+    T* dst = out + (m0 + row) * ld_row + c8 * 8;
+    if constexpr (sizeof(T) == 2) {
+      uint4 q;
+      __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) b[e] = __floats2bfloat162_rn(src[2 * e], src[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = q;
+    } else {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      d4[0] = make_float4(src[0], src[1], src[2], src[3]);
+      d4[1] = make_float4(src[4], src[5], src[6], src[7]);
+    }
+  }
+}
+
 // One warp per ray: each lane walks samples lane, lane+32, ...; dx is reduced over the ray.
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -189,6 +232,17 @@ int upnerf_points_posenc_fwd(const float* rays, const float* z, int64_t n_rays, 
                  UPNERF_ERR_BAD_SHAPE, "points_posenc_fwd: bad sizes");
   const unsigned grid = static_cast<unsigned>(ceil_div64(M, 128));
   LaunchScope scope(kCatPosenc, as_stream(stream));
+  const size_t es = dtype == UPNERF_BF16 ? 2 : 4;
+  if (width == 64 && (ld_out * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if (dtype == UPNERF_BF16)
+      points_posenc_fwd_tiled_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
+          rays, z, M, n_samples, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out);
+    else
+      points_posenc_fwd_tiled_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(
+          rays, z, M, n_samples, L, band_w, static_cast<float*>(out), ld_out);
+    UPNERF_CHECK_LAUNCH("points_posenc_fwd_tiled_kernel");
+    return UPNERF_OK;
+  }
   if (dtype == UPNERF_BF16)
     points_posenc_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
         rays, z, M, n_samples, L, band_w, static_cast<__nv_bfloat16*>(out), ld_out, width);

@@ -289,8 +289,14 @@ int mm(const Ctx& c, const float* A, int64_t sam, int64_t sak, const float* B, i
        int accumulate, int split_k = 1) {
   return upnerf_gemm_f32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
 }
+// out[n] += sum_m s[m] X[m,n] for fp32 X of any width (falls back to the GEMM for odd widths)
+int colsum_any(const float* X, int64_t ld, const float* sc, int64_t M, int N, float* out, cudaStream_t st) {
+  if (N % 128 == 0 || (N <= 256 && N % 2 == 0 && 256 % (N / 2) == 0))
+    return rowscale_colsum(X, ld, sc, M, N, out, nullptr, UPNERF_F32, st);
+  return upnerf_gemm_f32(sc, 0, 1, X, 1, ld, out, 0, 1, 1, N, M, nullptr, 0, 64, st);
+}
 int split_for(int64_t K) {
-  int64_t s = ceil_div64(K, 512);
+  int64_t s = ceil_div64(K, 128);
   if (s < 2) s = 2;
   if (s > 256) s = 256;
   return static_cast<int>(s);
@@ -490,14 +496,14 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   if (ph.feat) {
     const float* gf = io.g_feat;
     UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wsf, 1, W, s.gHFr, W, 1, R, W, L.F, nullptr, 0));
-    UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.bsf, 0, 1, s.gWs, 1, 0, R, 1, L.F, nullptr, 0));
+    UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bsf, nullptr, 0, s.gWs, c.st));
     UPNERF_TRY(mm(c, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
-    UPNERF_TRY(mm(c, p.Wsum, 0, 1, gf, 1, L.F, g + L.bsf, 0, 1, 1, L.F, R, nullptr, 0, split_for(R)));
+    UPNERF_TRY(colsum_any(gf, L.F, p.Wsum, R, L.F, g + L.bsf, c.st));
     if (ph.cand) {
       UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wcf, 1, H, s.gG2r, H, 1, R, H, L.F, nullptr, 0));
-      UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.bcf, 0, 1, s.gWc, 1, 0, R, 1, L.F, nullptr, 0));
+      UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bcf, nullptr, 0, s.gWc, c.st));
       UPNERF_TRY(mm(c, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
-      UPNERF_TRY(mm(c, p.Wcsum, 0, 1, gf, 1, L.F, g + L.bcf, 0, 1, 1, L.F, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(colsum_any(gf, L.F, p.Wcsum, R, L.F, g + L.bcf, c.st));
     }
   }
   const bool feat_grad = ph.feat;
