@@ -205,3 +205,35 @@ def test_render_rays_vs_oracle_1024(cuda_dev, tag, m, prog, precision):
     total = (num / den) ** 0.5
     print(f"[{precision} {tag}] parameter-gradient error: whole network {total:.2e}, worst tensor {worst:.2e}")
     assert total < gtol, total
+
+
+@pytest.mark.parametrize("name", list(NET_CASES))
+def test_nerf_forward_per_sample_api_golden(cuda_dev, name):
+    """`NeRF.forward(inputs, sched_mult)` (reference models/nerf.py:80-124), the per-sample API,
+    against the fixtures the real reference produced: same keys, values within 1e-4."""
+    from upnerf_b200.models.nerf import NeRF
+
+    kw, phases = NET_CASES[name]
+    g = load(f"nerf_forward_{name}")
+    cfg = O.NerfConfig(typ="coarse", **kw)
+    for tag, m, prog in phases:
+        mod = NeRF(cfg.typ, W=cfg.W, encode_feat=cfg.encode_feat, feat_dim=cfg.feat_dim, xyz_L=cfg.xyz_L, dir_L=cfg.dir_L,
+                   appearance_dim=cfg.appearance_dim, candidate_dim=cfg.candidate_dim, c2f=cfg.c2f)
+        mod.load_state_dict(synth.nerf_state(cfg, NET_SEEDS[name], progress=prog))
+        mod = mod.to(cuda_dev)
+        inputs = {"input_xyz": g["xyz"].to(cuda_dev), "input_dir": g["dirs"].to(cuda_dev)}
+        if cfg.encode_appearance:
+            inputs["input_a"] = g["a"].to(cuda_dev)
+        if cfg.encode_candidate:
+            inputs["input_c"] = g["c"].to(cuda_dev)
+        out = mod(inputs, sched_mult=m)
+        keys = {k.split("__")[1] for k in g if k.startswith(tag + "__")} - {"sched_mult", "progress"}
+        assert set(out) == keys
+        for k in keys:
+            ref = g[f"{tag}__{k}"]
+            assert out[k].shape == ref.shape
+            err = float((out[k].cpu() - ref).abs().max())
+            assert err <= 1e-4 * max(1.0, float(ref.abs().max())), (tag, k, err)
+        pe = mod.positional_encoding(inputs["input_xyz"], cfg.xyz_L).cpu()
+        ref_pe = O.positional_encoding(g["xyz"], cfg.xyz_L, prog, cfg.c2f)
+        assert float((pe - ref_pe).abs().max()) <= 1e-5      # same fp32 argument x*f_k, full-accuracy sincosf
