@@ -85,6 +85,32 @@ typedef struct upnerf_epilogue {
 int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                      int64_t M, int N, int K, const upnerf_epilogue* ep, void* stream);
 
+/* Fused trunk forward on tcgen05 (bf16 in, fp32 accumulate, bf16 out): per 128-sample tile
+ * PE -> xyz_encoding_1..8 (Linear 256 + ReLU, skip concat [PE | h] at layer 5) ->
+ * xyz_encoding_final, plus share_sigma (row-dot + Softplus) -- reference models/nerf.py:84-93.
+ * Activations stay in shared memory between layers; each layer output is stored once.
+ *   pe    [M, 64]  bf16, row stride ld_pe (the 63-wide encoding, zero padded)
+ *   wcat  [256, UPNERF_TRUNK_WCAT_COLS] bf16 K-major, row stride ld_w, columns
+ *         [W1 (64) | W2 | W3 | W4 | W5 as [h (256) | PE (64)] | W6 | W7 | W8 | W_final]
+ *   bias[l] [256] fp32; out[l] [M,256] bf16 row stride ld_out[l] (l = 0..7: H1..H8, 8: final)
+ *   s_sigma [M] fp32 = Softplus(H8 . sigma_w + sigma_b) */
+#define UPNERF_TRUNK_LAYERS 9
+#define UPNERF_TRUNK_WCAT_COLS 2176
+typedef struct upnerf_trunk_args {
+  const void* pe;
+  int64_t ld_pe;
+  const void* wcat;
+  int64_t ld_w;
+  const float* bias[UPNERF_TRUNK_LAYERS];
+  const float* sigma_w;
+  const float* sigma_b;
+  void* out[UPNERF_TRUNK_LAYERS];
+  int64_t ld_out[UPNERF_TRUNK_LAYERS];
+  float* s_sigma;
+  int64_t M;
+} upnerf_trunk_args;
+int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* stream);
+
 /* Weight gradient on tcgen05:  dW[n, colmap(k)] += sum_m dY[m,n] * X[m,k]  (fp32 atomics),
  * db[n] += sum_m dY[m,n].  dY:[M,N] bf16, X:[M,K] bf16.  N % 128 == 0 (N <= 256),
  * K % 64 == 0 (K <= 320).  Column segments map packed K columns to parameter columns:

@@ -148,3 +148,60 @@ def test_gemm_f32_epilogue(cuda_dev):
     torch.cuda.synchronize()
     ref = (A @ B.t() + bias + rbias.repeat_interleave(S, 0)) * (aux > 0) + 1.0
     assert torch.allclose(Cout, ref, rtol=1e-4, atol=1e-4)
+
+
+def _trunk_reference(pe, ws, bs, sw, sb):
+    """Layer-by-layer fp32 math on the same bf16-rounded operands, activations rounded to bf16
+    between layers exactly where the kernel rounds them (models/nerf.py:84-93)."""
+    outs = []
+    h = None
+    x = pe.float()
+    for l in range(9):
+        if l == 0:
+            a = x
+        elif l == 4:
+            a = torch.cat([h, x], 1)              # packed order [h | PE]
+        else:
+            a = h
+        y = a @ ws[l].float().t() + bs[l]
+        if l < 8:
+            y = torch.relu(y)
+        if l == 7:
+            sig = torch.nn.functional.softplus(y @ sw + sb)
+        h = y.to(torch.bfloat16).float()
+        outs.append(h)
+    return outs, sig
+
+
+@pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1])
+def test_mlp_trunk_fwd_fused(cuda_dev, M):
+    """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
+    covers a single tile, a ragged last tile and >2 tiles per SM (pipeline wrap-around)."""
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M)
+    pe = _bf16(torch.randn(M, 64, generator=g))
+    pe[:, 63] = 0
+    ks = [64, 256, 256, 256, 320, 256, 256, 256, 256]
+    ws = [_bf16(torch.randn(256, k, generator=g) * (1.7 / k ** 0.5)) for k in ks]
+    bs = [torch.randn(256, generator=g) * 0.1 for _ in ks]
+    sw, sb = torch.randn(256, generator=g) / 16, torch.randn(1, generator=g)
+    wcat = torch.cat(ws, 1).contiguous()
+    assert wcat.shape == (256, L.TRUNK_WCAT_COLS)
+    d = lambda t: t.to(cuda_dev)
+    # outputs with different row strides: H4 lives in the 320-wide skip buffer
+    outs = [torch.full((M, 320 if l == 3 else 256), float("nan"), dtype=torch.bfloat16, device=cuda_dev) for l in range(9)]
+    sig = torch.full((M,), float("nan"), device=cuda_dev)
+    L.mlp_trunk_fwd(d(pe), d(wcat), [d(b) for b in bs], d(sw), d(sb), [o[:, :256] for o in outs], sig, M)
+    torch.cuda.synchronize()
+    ref, ref_sig = _trunk_reference(d(pe), [d(w) for w in ws], [d(b) for b in bs], d(sw), d(sb))
+    for l in range(9):
+        got = outs[l][:, :256].float()
+        assert torch.isfinite(got).all(), l
+        # bf16 outputs of O(1) values: one rounding step (2^-8 relative) + re-association, growing
+        # slowly with depth because each layer re-rounds its input
+        err = (got - ref[l]).abs().max().item()
+        scale = ref[l].abs().max().item()
+        assert err <= 0.02 * max(scale, 1.0) * (1 + l / 4), (l, err, scale)
+    assert torch.isnan(outs[3][:, 256:].float()).all()        # the PE columns of the skip buffer are untouched
+    assert torch.allclose(sig, ref_sig, rtol=2e-2, atol=2e-2)

@@ -196,7 +196,9 @@ def test_sample_pdf_golden(cuda_dev):
         bound = 2e-5 + 4e-6 * cond
         assert (err <= bound).all(), float((err - bound).max())
         if i_key:
-            assert (inds.cpu() != g[i_key]).float().mean() < 0.02
+            # vs the reference's indices on ITS cdf: only ties can differ -- u = 1.0 of the det linspace
+            # against cdf[-1] = 1 +- 1 ulp is one per ray (the sample is the last bin either way)
+            assert (inds.cpu() != g[i_key]).float().mean() <= 1.0 / N + 1e-6
 
 
 def test_sample_pdf_module_api(cuda_dev):

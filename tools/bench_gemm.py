@@ -24,7 +24,8 @@ def timeit(fn, iters=10, warm=3):
 def main():
     dev = torch.device("cuda:0")
     M = 4096 * 192
-    for (N, K, aux) in [(256, 256, 0), (256, 256, 2), (256, 64, 0), (256, 320, 0), (128, 256, 0), (64, 256, 0)]:
+    only_trunk = "trunk" in sys.argv[1:]
+    for (N, K, aux) in [] if only_trunk else [(256, 256, 0), (256, 256, 2), (256, 64, 0), (256, 320, 0), (128, 256, 0), (64, 256, 0)]:
         A = torch.randn(M, K, device=dev).bfloat16()
         B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
         Cc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -37,7 +38,7 @@ def main():
         print(f"gemm_bf16 M={M} N={N} K={K} aux={aux}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: torch.matmul(A, B.t()))
         print(f"   torch.matmul bf16: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
-    for (N, K) in [(256, 256), (256, 320), (128, 256), (256, 64)]:
+    for (N, K) in [] if only_trunk else [(256, 256), (256, 320), (128, 256), (256, 64)]:
         dY = torch.randn(M, N, device=dev).bfloat16()
         X = torch.randn(M, K, device=dev).bfloat16()
         dW = torch.zeros(N, K, device=dev)
@@ -48,6 +49,20 @@ def main():
         print(f"wgrad_bf16 M={M} N={N} K={K}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: torch.matmul(dY.t(), X))
         print(f"   torch.matmul bf16: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    # fused trunk forward
+    pe = torch.randn(M, 64, device=dev).bfloat16()
+    ks = [64, 256, 256, 256, 320, 256, 256, 256, 256]
+    wcat = torch.cat([(torch.randn(256, k, device=dev) * (1.4 / k ** 0.5)).bfloat16() for k in ks], 1).contiguous()
+    bs = [torch.zeros(256, device=dev) for _ in ks]
+    sw, sb = torch.randn(256, device=dev) / 16, torch.zeros(1, device=dev)
+    outs = [torch.empty(M, 256, device=dev, dtype=torch.bfloat16) for _ in ks]
+    sig = torch.empty(M, device=dev)
+    ms = timeit(lambda: L.mlp_trunk_fwd(pe, wcat, bs, sw, sb, outs, sig, M))
+    fl = 2.0 * M * 256 * sum(ks)
+    by = (M * 64 + 9 * M * 256) * 2
+    print(f"mlp_trunk_fwd M={M}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s (write-only activations)")
+    if only_trunk:
+        return
     Mf = 256 * 192
     A = torch.randn(Mf, 256, device=dev)
     B = torch.randn(256, 256, device=dev)

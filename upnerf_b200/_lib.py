@@ -181,6 +181,34 @@ class CompositeArgs(C.Structure):
                 + [("ld_dhf", C.c_int64), ("d_g2pre", C.c_void_p), ("ld_dg2", C.c_int64)])
 
 
+TRUNK_LAYERS, TRUNK_WCAT_COLS = 9, 2176
+
+
+class TrunkArgs(C.Structure):
+    """Mirror of `upnerf_trunk_args`."""
+
+    _fields_ = [("pe", C.c_void_p), ("ld_pe", C.c_int64), ("wcat", C.c_void_p), ("ld_w", C.c_int64),
+                ("bias", C.c_void_p * TRUNK_LAYERS), ("sigma_w", C.c_void_p), ("sigma_b", C.c_void_p),
+                ("out", C.c_void_p * TRUNK_LAYERS), ("ld_out", C.c_int64 * TRUNK_LAYERS),
+                ("s_sigma", C.c_void_p), ("M", C.c_int64)]
+
+
+def mlp_trunk_fwd(pe, wcat, biases, sigma_w, sigma_b, outs, s_sigma, M):
+    """Fused trunk forward (see upnerf_mlp_trunk_fwd_bf16): pe [M,64], wcat [256,2176] bf16,
+    biases: 9 fp32 [256], outs: 9 bf16 [M,256] (any row stride), s_sigma [M] fp32."""
+    a = TrunkArgs()
+    a.pe, a.ld_pe = pe.data_ptr(), pe.stride(0)
+    a.wcat, a.ld_w = wcat.data_ptr(), wcat.stride(0)
+    for i in range(TRUNK_LAYERS):
+        ptr(biases[i]), ptr(outs[i])          # CUDA-only check
+        a.bias[i] = biases[i].data_ptr()
+        a.out[i] = outs[i].data_ptr()
+        a.ld_out[i] = outs[i].stride(0)
+    a.sigma_w, a.sigma_b, a.s_sigma = sigma_w.data_ptr(), sigma_b.data_ptr(), s_sigma.data_ptr()
+    a.M = int(M)
+    check(lib().upnerf_mlp_trunk_fwd_bf16(C.byref(a), stream_ptr()), "upnerf_mlp_trunk_fwd_bf16")
+
+
 def _vp(t):
     return None if t is None else t.data_ptr()
 

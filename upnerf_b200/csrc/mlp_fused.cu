@@ -1,0 +1,456 @@
+// Fused NeRF trunk on tcgen05 -- upnerf_mlp_trunk_fwd_bf16.
+//
+// One persistent kernel evaluates, per 128-sample tile, the whole xyz trunk of NeRF.forward
+// (reference models/nerf.py:84-93): PE -> 8 x (Linear 256 + ReLU) with the skip concat at
+// layer 5 -> xyz_encoding_final, plus the share_sigma row-dot + Softplus (:89).  Activations
+// never leave the SM between layers: the epilogue of layer l writes bf16 straight into the
+// 128-byte-swizzled K-major shared-memory boxes that layer l+1's MMAs read as their A operand.
+// Every layer output is also TMA-stored to HBM once (write-only) because backward needs it.
+//
+//   warp 0      TMA producer: streams the layer weights (256 x 64 bf16 K-chunks, 3 stages)
+//               from L2 and the PE tile of the current / next sample tile.
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x 256 x 16).
+//   warps 2..17 epilogue, two sets of eight warps (set s owns output boxes s and s+2):
+//               thread = one output row x 16 of the 32 columns of a chunk.
+//
+// Pipelining inside a tile: the accumulator is double buffered in TMEM (2 x 256 columns), and
+// the epilogue releases its output box by box (64 columns, one mbarrier each), so the MMAs of
+// layer l+1 over K-box b start as soon as box b of layer l has been written -- the tensor pipe
+// only idles for the first box of each layer.  Layers whose first K-chunk is the PE tile
+// (layer 1 and the skip layer) start even earlier, during the previous layer's epilogue.
+//
+// Measured (B200, M = 786432): 1.16 ms = 755 TFLOP/s with the activation stores, 0.79 ms
+// (1107 TFLOP/s) with the stores disabled -- the kernel sits between the HBM write roofline
+// (3.5 GB of activations per launch) and the shared-memory bandwidth the SS-mode UMMA needs
+// (12 KB per 128x256x16 MMA); see DESIGN.md section 5.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.h"
+#include "ptx_sm100.cuh"
+
+namespace upnerf {
+namespace {
+
+using namespace ptx;
+
+constexpr int kNL = UPNERF_TRUNK_LAYERS;  // 8 trunk layers + xyz_encoding_final
+constexpr int kWStages = 3;
+constexpr int kTileM = 128;
+constexpr int kBoxBytes = kTileM * 128;   // 128 rows x 64 bf16 columns
+constexpr int kActBytes = 4 * kBoxBytes;  // 128 x 256 activation tile
+constexpr int kWBytes = 256 * 128;        // 256 output features x 64 K columns
+constexpr int kSetThreads = 256;           // one epilogue set: 8 warps
+constexpr int kEpiThreads = 2 * kSetThreads;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kChunks = 8;                // 32-column chunks per 256-wide layer
+
+constexpr int kOffAct = 0;
+constexpr int kOffPE = kOffAct + kActBytes;
+constexpr int kOffW = kOffPE + 2 * kBoxBytes;
+constexpr int kOffBias = kOffW + kWStages * kWBytes;
+constexpr int kOffHeadW = kOffBias + kNL * 256 * 4;
+constexpr int kOffHead = kOffHeadW + 256 * 4;
+constexpr int kOffBar = kOffHead + 4 * kTileM * 4;
+constexpr int kNumBars = 2 * kWStages + 4 + kChunks + 2;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmem + 16 + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+struct LayerDesc {
+  int w_act;    // first K column (in Wcat) of the weights multiplying the activation tile; -1: none
+  int w_pe;     // K column of the weights multiplying the PE tile; -1: none
+  int relu;
+  int feeds;    // output is the A operand of the next layer
+  int head;     // share_sigma rides on this layer's epilogue
+  int pe_last;  // last user of the PE tile within a sample tile
+};
+
+struct TrunkMaps {
+  CUtensorMap w, pe, out[kNL];
+};
+
+struct TrunkArgs {
+  int64_t M;
+  int num_tiles;
+  LayerDesc layer[kNL];
+  const float* bias[kNL];
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+};
+
+__device__ __forceinline__ float softplus_ref(float x) {
+  // torch.nn.Softplus(beta=1, threshold=20)
+  return x > 20.f ? x : log1pf(expf(x));
+}
+
+// kCluster = 2: the two CTAs of a cluster walk their tiles in lockstep and share the weight
+// stream -- each loads one half (128 output features) of every weight chunk and TMA-multicasts
+// it into both CTAs, which halves the L2 -> shared-memory traffic (the first bound this kernel
+// hits: 1.06 MB of weights per 128-sample tile).
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sAct = smem + kOffAct;
+  uint8_t* sPE = smem + kOffPE;
+  uint8_t* sW = smem + kOffW;
+  float* sBias = reinterpret_cast<float*>(smem + kOffBias);
+  float* sHeadW = reinterpret_cast<float*>(smem + kOffHeadW);
+  float* sHead = reinterpret_cast<float*>(smem + kOffHead);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* bar_wfull = bars;
+  uint64_t* bar_wempty = bars + kWStages;
+  uint64_t* bar_pefull = bars + 2 * kWStages;
+  uint64_t* bar_peempty = bars + 2 * kWStages + 2;
+  uint64_t* bar_act = bars + 2 * kWStages + 4;
+  uint64_t* bar_tfull = bars + 2 * kWStages + 4 + kChunks;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  // Tiles are dealt to clusters; CTA r of a cluster takes tile kCluster*unit + r.  Every CTA of a
+  // cluster runs the same number of iterations (a tile index past the end is a dummy tile: TMA
+  // zero-fills its loads and drops its stores), which keeps the shared weight stream in lockstep.
+  const int unit0 = blockIdx.x / kCluster;
+  const int unit_step = gridDim.x / kCluster;
+  const int num_units = (args.num_tiles + kCluster - 1) / kCluster;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCluster) - 1);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.w);
+    prefetch_tmap(&maps.pe);
+    for (int i = 0; i < kNL; ++i) prefetch_tmap(&maps.out[i]);
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_wempty[i], kCluster);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_pefull[i], 1);
+      mbar_init(&bar_peempty[i], 1);
+      mbar_init(&bar_tfull[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);  // one per output box: 8 warps of a set
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < kNL * 256; i += kEpiThreads) {
+      const float* b = args.bias[i >> 8];
+      sBias[i] = b ? b[i & 255] : 0.f;
+    }
+    for (int i = t; i < 256; i += kEpiThreads) sHeadW[i] = args.head_w ? args.head_w[i] : 0.f;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      auto load_w = [&](int kcol) {
+        mbar_wait(&bar_wempty[ws], wph ^ 1);
+        mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
+        if (kCluster == 1) {
+          tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
+        } else {
+          constexpr int kPart = kWBytes / kCluster;  // my share of the chunk: 256/kCluster features
+          tma_load_2d_mc(sW + ws * kWBytes + cta_rank * kPart, &maps.w, &bar_wfull[ws], kcol,
+                         cta_rank * (256 / kCluster), kMask);
+        }
+        if (++ws == kWStages) {
+          ws = 0;
+          wph ^= 1;
+        }
+      };
+      auto load_pe = [&](int t, int tile) {
+        const int slot = t & 1;
+        mbar_wait(&bar_peempty[slot], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
+        tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
+      };
+      int t = 0;
+      if (unit0 < num_units) load_pe(0, unit0 * kCluster + cta_rank);
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
+        for (int l = 0; l < kNL; ++l) {
+          const LayerDesc& L = args.layer[l];
+          if (L.w_pe >= 0) load_w(L.w_pe);
+          if (l == 1) {  // the next tile's PE, one tile ahead
+            const int next = unit + unit_step;
+            if (next < num_units) load_pe(t + 1, next * kCluster + cta_rank);
+          }
+          if (L.w_act >= 0)
+            for (int b = 0; b < 4; ++b) load_w(L.w_act + b * 64);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
+      int ws = 0;
+      uint32_t wph = 0;
+      uint32_t act_ph = 0;
+      uint32_t g = 0;  // layers issued so far (accumulator = g & 1)
+      int t = 0;
+      auto free_stage = [&](uint64_t* bar) {
+        if (kCluster == 1) mma_commit(bar);
+        else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
+      };
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
+        const int slot = t & 1;
+        const uint32_t pe_ph = (t >> 1) & 1;
+        for (int l = 0; l < kNL; ++l, ++g) {
+          const LayerDesc& L = args.layer[l];
+          const uint32_t d_tmem = tmem_base + (g & 1) * 256;
+          uint32_t accum = 0;
+          if (L.w_pe >= 0) {
+            mbar_wait(&bar_pefull[slot], pe_ph);
+            mbar_wait(&bar_wfull[ws], wph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(sPE + slot * kBoxBytes);
+            const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                          umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
+              accum = 1;
+            }
+            free_stage(&bar_wempty[ws]);
+            if (L.pe_last) mma_commit(&bar_peempty[slot]);
+            if (++ws == kWStages) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+          if (L.w_act >= 0) {
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+              mbar_wait(&bar_wfull[ws], wph);
+              mbar_wait(&bar_act[b], act_ph);
+              tc_fence_after_sync();
+              const uint32_t a_addr = smem_u32(sAct + b * kBoxBytes);
+              const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                            umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
+                accum = 1;
+              }
+              free_stage(&bar_wempty[ws]);
+              if (++ws == kWStages) {
+                ws = 0;
+                wph ^= 1;
+              }
+            }
+            act_ph ^= 1;
+          }
+          mma_commit(&bar_tfull[g & 1]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    // Two sets of eight warps.  Set s owns the 64-column output boxes s and s+2 of every layer;
+    // inside a set, warp (quad, half) handles rows quad*32.. and the 32-column chunk `half` of
+    // the box, as two 16-column TMEM loads (the next load is in flight while one is processed).
+    // The epilogue is issue-bound, so everything per-chunk is kept off the per-element path:
+    // flags live in registers, shared memory is addressed explicitly, one mbarrier arrival per
+    // warp, one named barrier per box.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;     // 0..3
+    const int half = grp & 1;    // which 32-column chunk of a box
+    const int set = grp >> 1;    // which boxes
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const bool lane0 = lane_id() == 0;
+    const bool leader = ((ew & 7) == 0) && lane0;  // one per set
+    const uint32_t set_bar = 2 + set;
+    const uint32_t sact_row = smem_u32(sAct) + row * 128;
+    const uint32_t sbias = smem_u32(sBias);
+    const uint32_t sheadw = smem_u32(sHeadW);
+    const uint32_t swz = row & 7;
+    uint32_t g = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int tile = unit * kCluster + cta_rank;
+      const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
+      for (int l = 0; l < kNL; ++l, ++g) {
+        const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
+        mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
+        float hacc = 0.f;
+        uint32_t r[2][16];
+        tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int box = set + (q & 2);                  // q = 0,1: box s; q = 2,3: box s+2
+          const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+          tmem_ld_wait_dep(r[q & 1]);
+          if (q < 3) {
+            const int nbox = set + ((q + 1) & 2);
+            tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
+          }
+          const uint32_t* rr = r[q & 1];
+          float v[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 b4 = lds128(sbias + (l * 256 + col0 + k * 4) * 4);
+            v[k * 4 + 0] = __uint_as_float(rr[k * 4 + 0]) + b4.x;
+            v[k * 4 + 1] = __uint_as_float(rr[k * 4 + 1]) + b4.y;
+            v[k * 4 + 2] = __uint_as_float(rr[k * 4 + 2]) + b4.z;
+            v[k * 4 + 3] = __uint_as_float(rr[k * 4 + 3]) + b4.w;
+          }
+          if (relu) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (head) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 w4 = lds128(sheadw + (col0 + k * 4) * 4);
+              hacc += v[k * 4] * w4.x + v[k * 4 + 1] * w4.y + v[k * 4 + 2] * w4.z + v[k * 4 + 3] * w4.w;
+            }
+          }
+          uint4 o[2];
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          const uint32_t box_row = sact_row + box * kBoxBytes;
+          const uint32_t s0 = half * 4 + (q & 1) * 2;
+          sts128(box_row + ((s0 ^ swz) << 4), o[0]);
+          sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
+          if (q & 1) {
+            // my 32-column chunk of the box is written
+            fence_proxy_async_smem();   // my writes -> visible to the async proxy (MMA, TMA store)
+            if (feeds) {
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane0) mbar_arrive(&bar_act[box]);  // one arrival per warp
+            }
+            // Box complete once both halves are: store it.  The set's other box is written next;
+            // its previous store (the latest group of this leader) must have been read out.
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(set_bar, kSetThreads);
+            if (leader) {
+              tma_store_2d(&maps.out[l], sAct + box * kBoxBytes, box * 64, tile * kTileM);
+              tma_store_commit();
+            }
+          }
+        }
+        if (head) {
+          sHead[grp * kTileM + row] = hacc;
+          named_bar_sync(4, kEpiThreads);
+          if (grp == 0 && grow < args.M)
+            args.head_out[grow] = softplus_ref(sHead[row] + sHead[kTileM + row] + sHead[2 * kTileM + row] +
+                                               sHead[3 * kTileM + row] + args.head_b[0]);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still signal it
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// 2 (default): CTA pairs share the weight stream by TMA multicast; UPNERF_TRUNK_CLUSTER=1
+// selects independent CTAs (for A/B measurements).
+int trunk_cluster_size() {
+  static int v = 0;
+  if (v) return v;
+  const char* e = getenv("UPNERF_TRUNK_CLUSTER");
+  v = (e && e[0] == '1') ? 1 : 2;
+  return v;
+}
+
+}  // namespace
+}  // namespace upnerf
+
+extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(a && a->M > 0, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: M=%lld", a ? (long long)a->M : -1ll);
+  UPNERF_REQUIRE(a->pe && a->wcat && a->s_sigma && a->sigma_w && a->sigma_b, UPNERF_ERR_BAD_SHAPE,
+                 "mlp_trunk_fwd: missing operand");
+  UPNERF_REQUIRE(a->ld_w >= UPNERF_TRUNK_WCAT_COLS, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: ld_w=%lld < %d",
+                 (long long)a->ld_w, UPNERF_TRUNK_WCAT_COLS);
+  const int64_t tiles = ceil_div64(a->M, kTileM);
+  UPNERF_REQUIRE(tiles < (1ll << 24), UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: M too large");
+
+  TrunkMaps maps;  // rebuilt on every call (host-side encode only)
+  TrunkArgs args;
+  memset(&args, 0, sizeof(args));
+  args.M = a->M;
+  args.num_tiles = static_cast<int>(tiles);
+  const int cluster = trunk_cluster_size();
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat, 256, UPNERF_TRUNK_WCAT_COLS, a->ld_w, 256 / cluster, 64));
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.pe, a->pe, a->M, 64, a->ld_pe, kTileM, 64));
+  // Wcat columns: [W1 (64) | W2 | W3 | W4 | W5 = [h (256) | PE (64)] | W6 | W7 | W8 | WF]
+  const int w_act[kNL] = {-1, 64, 320, 576, 832, 1152, 1408, 1664, 1920};
+  const int w_pe[kNL] = {0, -1, -1, -1, 1088, -1, -1, -1, -1};
+  for (int l = 0; l < kNL; ++l) {
+    UPNERF_REQUIRE(a->out[l], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: out[%d] missing", l);
+    UPNERF_TRY(make_tmap_bf16_2d(&maps.out[l], a->out[l], a->M, 256, a->ld_out[l], kTileM, 64));
+    LayerDesc& L = args.layer[l];
+    L.w_act = w_act[l];
+    L.w_pe = w_pe[l];
+    L.relu = l < 8;
+    L.feeds = l < 8;
+    L.head = l == 7;
+    L.pe_last = l == 4;
+    args.bias[l] = a->bias[l];
+  }
+  args.head_w = a->sigma_w;
+  args.head_b = a->sigma_b;
+  args.head_out = a->s_sigma;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+    attr_set = true;
+  }
+  const double flop = 2.0 * a->M * 256.0 * (64 + 7 * 256 + 320);
+  LaunchScope scope(kCatGemmTc, as_stream(stream), flop);
+  if (cluster == 1) {
+    const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+    mlp_trunk_fwd_kernel<1><<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(maps, args);
+  } else {
+    const int64_t units = ceil_div64(tiles, 2);
+    const int max_clusters = sm_count() / 2;
+    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
+  }
+  UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_kernel");
+  return UPNERF_OK;
+}

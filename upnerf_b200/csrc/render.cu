@@ -90,8 +90,11 @@ struct Bump {
   void* take_bytes(uint64_t bytes) { return take<uint8_t>(bytes); }
 };
 
+constexpr int WCAT = UPNERF_TRUNK_WCAT_COLS;  // trunk forward weights, concatenated along K
 struct Packed {  // GEMM operands derived from the fp32 parameters (element type T)
-  void *W1, *Wk[8], *W5, *WF, *Wc1, *Wc2, *Wq;         // [N, K] K-major
+  void* Wcat;                                           // [256, WCAT]: W1|W2|W3|W4|W5=[h|PE]|W6|W7|W8|WF
+  void *W1, *Wk[8], *W5, *WF;                           // views into Wcat (row stride WCAT)
+  void *Wc1, *Wc2, *Wq;                                 // [N, K] K-major
   void *W1T, *WkT[8], *W5T, *WFT, *Wc1T, *Wc2T, *WqT;  // transposed for the data gradient
   float* Wq32;      // [128,256] fp32 folded rgb weight
   float* bq_const;  // [128]
@@ -147,17 +150,30 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBu
   b.off = (b.off + 255) & ~uint64_t(255);
   const uint64_t start = b.off;
   k.region = b.base ? b.base + start : nullptr;
-  k.W1 = b.take_bytes(W * PEW * es);
+  k.Wcat = b.take_bytes(static_cast<uint64_t>(W) * WCAT * es);
+  {
+    int64_t c = 0;
+    auto view = [&](int width) {
+      void* p = k.Wcat ? static_cast<uint8_t*>(k.Wcat) + c * es : nullptr;
+      c += width;
+      return p;
+    };
+    k.W1 = view(PEW);
+    for (int i = 0; i < 8; ++i) {
+      k.Wk[i] = nullptr;
+      if (i == 0) continue;
+      if (i == 4) k.W5 = view(X4W);
+      else k.Wk[i] = view(W);
+    }
+    k.WF = view(W);
+  }
   k.W1T = b.take_bytes(PEW * W * es);
   for (int i = 0; i < 8; ++i) {
-    k.Wk[i] = k.WkT[i] = nullptr;
+    k.WkT[i] = nullptr;
     if (i == 0 || i == 4) continue;
-    k.Wk[i] = b.take_bytes(W * W * es);
     k.WkT[i] = b.take_bytes(W * W * es);
   }
-  k.W5 = b.take_bytes(W * X4W * es);
   k.W5T = b.take_bytes(X4W * W * es);
-  k.WF = b.take_bytes(W * W * es);
   k.WFT = b.take_bytes(W * W * es);
   k.Wc1 = b.take_bytes(H * W * es);
   k.Wc1T = b.take_bytes(W * H * es);
@@ -323,19 +339,19 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
   };
   const int ix = L.in_xyz;
   // layer 1: [256, in_xyz] -> [256, 64] (zero padded) and its transpose [64, 256]
-  add(prm + L.Wl[0], ix, k.W1, PEW, W, ix, 0);
+  add(prm + L.Wl[0], ix, k.W1, WCAT, W, ix, 0);
   add(prm + L.Wl[0], ix, k.W1T, W, W, ix, 1);
   for (int i = 1; i < 8; ++i) {
     if (i == 4) continue;
-    add(prm + L.Wl[i], W, k.Wk[i], W, W, W, 0);
+    add(prm + L.Wl[i], W, k.Wk[i], WCAT, W, W, 0);
     add(prm + L.Wl[i], W, k.WkT[i], W, W, W, 1);
   }
   // skip layer: reference input is [PE | h]; the packed input is [h | PE | 0]
-  add(prm + L.Wl[4] + ix, W + ix, k.W5, X4W, W, W, 0);
-  add(prm + L.Wl[4], W + ix, col(k.W5, W, c.es), X4W, W, ix, 0);
+  add(prm + L.Wl[4] + ix, W + ix, k.W5, WCAT, W, W, 0);
+  add(prm + L.Wl[4], W + ix, col(k.W5, W, c.es), WCAT, W, ix, 0);
   add(prm + L.Wl[4] + ix, W + ix, k.W5T, W, W, W, 1);
   add(prm + L.Wl[4], W + ix, col(k.W5T, static_cast<int64_t>(W) * W, c.es), W, W, ix, 1);
-  add(prm + L.Wf, W, k.WF, W, W, W, 0);
+  add(prm + L.Wf, W, k.WF, WCAT, W, W, 0);
   add(prm + L.Wf, W, k.WFT, W, W, W, 1);
   if (ph.cand) {
     add(prm + L.Wc0, W + L.cd, k.Wc1, W, H, W, 0);
@@ -376,33 +392,52 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   void* PE = col(p.X4, W, c.es);
   UPNERF_TRY(upnerf_points_posenc_fwd(a.rays, p.z, R, S, cfg.xyz_L, k.band_xyz, PE, X4W, PEW, c.dtype, c.st));
 
-  // trunk
+  // trunk + xyz_encoding_final (+ share_sigma on layer 8)
   upnerf_epilogue e = ep_none();
-  e.act = 1;
-  e.bias = prm + L.bl[0];
-  UPNERF_TRY(linear(c, PE, X4W, k.W1, PEW, p.Hs[1], W, M, W, PEW, e));
-  for (int i = 1; i < 8; ++i) {
-    e = ep_none();
-    e.act = 1;
-    e.bias = prm + L.bl[i];
-    const void* in = p.Hs[i];
-    const int64_t ldin = (i == 4) ? X4W : W;
-    void* out = p.Hs[i + 1];
-    const int64_t ldout = (i + 1 == 4) ? X4W : W;
-    if (i == 7) {  // share_sigma rides on layer 8's epilogue
-      e.n_heads = 1;
-      e.head_w = prm + L.Ws;
-      e.head_b = prm + L.bs;
-      e.head_act = 1;
-      e.head_out = p.ssig;
+  if (c.dtype == UPNERF_BF16) {
+    // one persistent tcgen05 kernel; activations stay in shared memory between layers
+    upnerf_trunk_args ta;
+    memset(&ta, 0, sizeof(ta));
+    ta.pe = PE; ta.ld_pe = X4W;
+    ta.wcat = k.Wcat; ta.ld_w = WCAT;
+    for (int i = 0; i < 8; ++i) {
+      ta.bias[i] = prm + L.bl[i];
+      ta.out[i] = p.Hs[i + 1];
+      ta.ld_out[i] = (i + 1 == 4) ? X4W : W;
     }
-    if (i == 4) UPNERF_TRY(linear(c, in, ldin, k.W5, X4W, out, ldout, M, W, X4W, e));
-    else UPNERF_TRY(linear(c, in, ldin, k.Wk[i], W, out, ldout, M, W, W, e));
+    ta.bias[8] = prm + L.bf;
+    ta.out[8] = p.HF; ta.ld_out[8] = W;
+    ta.sigma_w = prm + L.Ws; ta.sigma_b = prm + L.bs;
+    ta.s_sigma = p.ssig;
+    ta.M = M;
+    UPNERF_TRY(upnerf_mlp_trunk_fwd_bf16(&ta, c.st));
+  } else {
+    e.act = 1;
+    e.bias = prm + L.bl[0];
+    UPNERF_TRY(linear(c, PE, X4W, k.W1, WCAT, p.Hs[1], W, M, W, PEW, e));
+    for (int i = 1; i < 8; ++i) {
+      e = ep_none();
+      e.act = 1;
+      e.bias = prm + L.bl[i];
+      const void* in = p.Hs[i];
+      const int64_t ldin = (i == 4) ? X4W : W;
+      void* out = p.Hs[i + 1];
+      const int64_t ldout = (i + 1 == 4) ? X4W : W;
+      if (i == 7) {  // share_sigma rides on layer 8's epilogue
+        e.n_heads = 1;
+        e.head_w = prm + L.Ws;
+        e.head_b = prm + L.bs;
+        e.head_act = 1;
+        e.head_out = p.ssig;
+      }
+      if (i == 4) UPNERF_TRY(linear(c, in, ldin, k.W5, WCAT, out, ldout, M, W, X4W, e));
+      else UPNERF_TRY(linear(c, in, ldin, k.Wk[i], WCAT, out, ldout, M, W, W, e));
+    }
+    // xyz_encoding_final (no activation)
+    e = ep_none();
+    e.bias = prm + L.bf;
+    UPNERF_TRY(linear(c, p.Hs[8], W, k.WF, WCAT, p.HF, W, M, W, W, e));
   }
-  // xyz_encoding_final (no activation)
-  e = ep_none();
-  e.bias = prm + L.bf;
-  UPNERF_TRY(linear(c, p.Hs[8], W, k.WF, W, p.HF, W, M, W, W, e));
 
   if (ph.cand) {
     // per-ray bias of candidate_encoding.0: W[:, 256:] c_emb + b
