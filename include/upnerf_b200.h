@@ -108,8 +108,35 @@ typedef struct upnerf_trunk_args {
   int64_t ld_out[UPNERF_TRUNK_LAYERS];
   float* s_sigma;
   int64_t M;
+  uint32_t* relu_mask; /* optional [upnerf_trunk_mask_words(M)]: ReLU bit masks of H1..H8 for the backward chain */
 } upnerf_trunk_args;
 int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* stream);
+int64_t upnerf_trunk_mask_words(int64_t M);
+
+/* Fused backward data-gradient chain of the trunk (autograd backward of models/nerf.py:84-93
+ * with respect to the activations), one persistent tcgen05 kernel:
+ *   dY8 = (d_hf . W_final + d_ssig (x) sigma_w) * [H8 > 0];  dYl = (dY(l+1) . W(l+1)[h part]) * [Hl > 0]
+ *   d_hf   [M,256] bf16 (gradient of xyz_encoding_final's output), d_ssig [M] fp32 (gradient of
+ *          the pre-Softplus sigma, may be NULL)
+ *   wcat_t [256, UPNERF_TRUNK_WCATT_COLS] bf16, row n = input feature, columns
+ *          [W_final^T | W8^T | W7^T | W6^T | W5[h part]^T | W4^T | W3^T | W2^T]
+ *   relu_mask: written by upnerf_mlp_trunk_fwd_bf16 on the same M
+ *   d_out[j] [M,256] bf16 = dY(8-j), j = 0..7 (gradient w.r.t. the pre-activation of layer 8-j) */
+#define UPNERF_TRUNK_BWD_LAYERS 8
+#define UPNERF_TRUNK_WCATT_COLS 2048
+typedef struct upnerf_trunk_bwd_args {
+  const void* d_hf;
+  int64_t ld_dhf;
+  const float* d_ssig;
+  const float* sigma_w;
+  const void* wcat_t;
+  int64_t ld_w;
+  const uint32_t* relu_mask;
+  void* d_out[UPNERF_TRUNK_BWD_LAYERS];
+  int64_t ld_dout[UPNERF_TRUNK_BWD_LAYERS];
+  int64_t M;
+} upnerf_trunk_bwd_args;
+int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* stream);
 
 /* Weight gradient on tcgen05:  dW[n, colmap(k)] += sum_m dY[m,n] * X[m,k]  (fp32 atomics),
  * db[n] += sum_m dY[m,n].  dY:[M,N] bf16, X:[M,K] bf16.  N % 128 == 0 (N <= 256),

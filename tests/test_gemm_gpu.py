@@ -205,3 +205,46 @@ def test_mlp_trunk_fwd_fused(cuda_dev, M):
         assert err <= 0.02 * max(scale, 1.0) * (1 + l / 4), (l, err, scale)
     assert torch.isnan(outs[3][:, 256:].float()).all()        # the PE columns of the skip buffer are untouched
     assert torch.allclose(sig, ref_sig, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M", [128 * 2 + 77, 128 * 148 * 2 + 128 * 3 + 9])
+def test_mlp_trunk_bwd_fused(cuda_dev, M):
+    """Fused backward chain: dY8 = (dHF W_F + dssig (x) w_s) * [H8>0], dYl = (dY(l+1) W(l+1)) * [Hl>0],
+    with the ReLU bit masks written by the fused forward, against layer-wise fp32 math on the same
+    bf16 operands (masks taken from the forward kernel's own activations, so no mask can flip)."""
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M + 1)
+    d = lambda t: t.to(cuda_dev)
+    pe = _bf16(torch.randn(M, 64, generator=g))
+    pe[:, 63] = 0
+    ks = [64, 256, 256, 256, 320, 256, 256, 256, 256]
+    ws = [d(_bf16(torch.randn(256, k, generator=g) * (1.7 / k ** 0.5))) for k in ks]
+    bs = [d(torch.randn(256, generator=g) * 0.1) for _ in ks]
+    sw, sb = d(torch.randn(256, generator=g) / 16), d(torch.randn(1, generator=g))
+    wcat = torch.cat(ws, 1).contiguous()
+    outs = [torch.empty(M, 256, dtype=torch.bfloat16, device=cuda_dev) for _ in ks]
+    sig = torch.empty(M, device=cuda_dev)
+    mask = torch.zeros(L.trunk_mask_words(M), dtype=torch.int32, device=cuda_dev)
+    L.mlp_trunk_fwd(d(pe), wcat, bs, sw, sb, outs, sig, M, relu_mask=mask)
+    # transposed weights in chain order: WF | W8 | W7 | W6 | W5[h part] | W4 | W3 | W2, each [in, out]
+    chain = [ws[8], ws[7], ws[6], ws[5], ws[4][:, :256], ws[3], ws[2], ws[1]]
+    wcat_t = torch.cat([w.t().contiguous() for w in chain], 1).contiguous()
+    assert wcat_t.shape == (256, L.TRUNK_WCATT_COLS)
+    d_hf = d(_bf16(torch.randn(M, 256, generator=g)))
+    d_ssig = d(torch.randn(M, generator=g))
+    d_outs = [torch.full((M, 256), float("nan"), dtype=torch.bfloat16, device=cuda_dev) for _ in range(8)]
+    L.mlp_trunk_bwd(d_hf, d_ssig, sw, wcat_t, mask, d_outs, M)
+    torch.cuda.synchronize()
+    cur = d_hf.float()
+    for j in range(8):
+        y = cur @ chain[j].float()                      # [M, out] @ [out, in]
+        if j == 0:
+            y = y + d_ssig[:, None] * sw[None, :]
+        y = y * (outs[7 - j].float() > 0)
+        got = d_outs[j].float()
+        assert torch.isfinite(got).all(), j
+        err = (got - y).abs().max().item()
+        assert err <= 0.02 * max(y.abs().max().item(), 1.0), (j, err)
+        assert ((got != 0) <= (outs[7 - j].float() > 0)).all(), j      # the mask is exact
+        cur = got                                        # chain on the kernel's own bf16 output

@@ -190,10 +190,43 @@ class TrunkArgs(C.Structure):
     _fields_ = [("pe", C.c_void_p), ("ld_pe", C.c_int64), ("wcat", C.c_void_p), ("ld_w", C.c_int64),
                 ("bias", C.c_void_p * TRUNK_LAYERS), ("sigma_w", C.c_void_p), ("sigma_b", C.c_void_p),
                 ("out", C.c_void_p * TRUNK_LAYERS), ("ld_out", C.c_int64 * TRUNK_LAYERS),
-                ("s_sigma", C.c_void_p), ("M", C.c_int64)]
+                ("s_sigma", C.c_void_p), ("M", C.c_int64), ("relu_mask", C.c_void_p)]
 
 
-def mlp_trunk_fwd(pe, wcat, biases, sigma_w, sigma_b, outs, s_sigma, M):
+TRUNK_BWD_LAYERS, TRUNK_WCATT_COLS = 8, 2048
+
+
+class TrunkBwdArgs(C.Structure):
+    """Mirror of `upnerf_trunk_bwd_args`."""
+
+    _fields_ = [("d_hf", C.c_void_p), ("ld_dhf", C.c_int64), ("d_ssig", C.c_void_p), ("sigma_w", C.c_void_p),
+                ("wcat_t", C.c_void_p), ("ld_w", C.c_int64), ("relu_mask", C.c_void_p),
+                ("d_out", C.c_void_p * TRUNK_BWD_LAYERS), ("ld_dout", C.c_int64 * TRUNK_BWD_LAYERS),
+                ("M", C.c_int64)]
+
+
+def trunk_mask_words(M: int) -> int:
+    f = lib().upnerf_trunk_mask_words
+    f.restype = C.c_int64
+    return int(f(_i64(M)))
+
+
+def mlp_trunk_bwd(d_hf, d_ssig, sigma_w, wcat_t, relu_mask, d_outs, M):
+    """Fused backward data-gradient chain (see upnerf_mlp_trunk_bwd_bf16): d_outs = [dY8, ..., dY1]."""
+    a = TrunkBwdArgs()
+    a.d_hf, a.ld_dhf = ptr(d_hf).value, d_hf.stride(0)
+    a.d_ssig = None if d_ssig is None else ptr(d_ssig).value
+    a.sigma_w = ptr(sigma_w).value
+    a.wcat_t, a.ld_w = ptr(wcat_t).value, wcat_t.stride(0)
+    a.relu_mask = ptr(relu_mask).value
+    for j in range(TRUNK_BWD_LAYERS):
+        a.d_out[j] = ptr(d_outs[j]).value
+        a.ld_dout[j] = d_outs[j].stride(0)
+    a.M = int(M)
+    check(lib().upnerf_mlp_trunk_bwd_bf16(C.byref(a), stream_ptr()), "upnerf_mlp_trunk_bwd_bf16")
+
+
+def mlp_trunk_fwd(pe, wcat, biases, sigma_w, sigma_b, outs, s_sigma, M, relu_mask=None):
     """Fused trunk forward (see upnerf_mlp_trunk_fwd_bf16): pe [M,64], wcat [256,2176] bf16,
     biases: 9 fp32 [256], outs: 9 bf16 [M,256] (any row stride), s_sigma [M] fp32."""
     a = TrunkArgs()
@@ -206,6 +239,7 @@ def mlp_trunk_fwd(pe, wcat, biases, sigma_w, sigma_b, outs, s_sigma, M):
         a.ld_out[i] = outs[i].stride(0)
     a.sigma_w, a.sigma_b, a.s_sigma = sigma_w.data_ptr(), sigma_b.data_ptr(), s_sigma.data_ptr()
     a.M = int(M)
+    a.relu_mask = None if relu_mask is None else ptr(relu_mask).value
     check(lib().upnerf_mlp_trunk_fwd_bf16(C.byref(a), stream_ptr()), "upnerf_mlp_trunk_fwd_bf16")
 
 

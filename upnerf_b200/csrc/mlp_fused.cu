@@ -79,6 +79,7 @@ struct TrunkArgs {
   const float* head_w;
   const float* head_b;
   float* head_out;
+  uint32_t* relu_mask;  // [tiles][8 layers][8 chunks][128 rows] or nullptr
 };
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -289,6 +290,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
         mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
+        const bool want_mask = relu && args.relu_mask != nullptr;
+        uint32_t mbits = 0;
         float hacc = 0.f;
         uint32_t r[2][16];
         tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
@@ -330,8 +333,21 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
           const uint32_t s0 = half * 4 + (q & 1) * 2;
           sts128(box_row + ((s0 ^ swz) << 4), o[0]);
           sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
+          if (want_mask) {
+            // ReLU mask of the stored (bf16) activations: bit e = column e of my 32-column chunk
+            const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
+            uint32_t m16 = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              m16 |= ((ow[e] & 0xFFFFu) ? 1u : 0u) << (2 * e);
+              m16 |= ((ow[e] >> 16) ? 1u : 0u) << (2 * e + 1);
+            }
+            mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
+          }
           if (q & 1) {
             // my 32-column chunk of the box is written
+            if (want_mask)
+              args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
             fence_proxy_async_smem();   // my writes -> visible to the async proxy (MMA, TMA store)
             if (feeds) {
               tc_fence_before_sync();
@@ -368,6 +384,272 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+// =====================================================================================
+// Backward data-gradient chain of the trunk -- upnerf_mlp_trunk_bwd_bf16.
+//
+//   dY8 = (dHF . W_final + d_ssig (x) w_sigma) * [H8 > 0]          (layer index j = 0)
+//   dYl = (dY(l+1) . W(l+1)[:, h part]) * [Hl > 0],  l = 7..1      (j = 1..7)
+//
+// i.e. the autograd backward of models/nerf.py:84-93 with respect to the activations; the
+// weight gradients are separate launches that read the dY tensors this kernel stores.  Same
+// structure as the forward kernel: the gradient tile stays in shared memory between layers
+// (in place), weights (transposed) stream through 3 TMA stages shared by the CTA pair, the
+// accumulator is double buffered in TMEM.  The ReLU masks are the bit masks the forward kernel
+// wrote (32 B per sample and layer instead of re-reading 512 B of activations).  The incoming
+// dHF tile lands in its own 64 KB buffer, prefetched one tile ahead.
+namespace bwd {
+
+constexpr int kNLb = UPNERF_TRUNK_BWD_LAYERS;  // 8
+constexpr int kOffIn = 0;
+constexpr int kOffActB = kOffIn + kActBytes;
+constexpr int kOffWB = kOffActB + kActBytes;
+constexpr int kOffSigW = kOffWB + kWStages * kWBytes;
+constexpr int kOffBarB = kOffSigW + 256 * 4;
+constexpr int kNumBarsB = 2 * kWStages + 2 + 4 + 2;
+constexpr int kOffTmemB = kOffBarB + kNumBarsB * 8;
+constexpr int kSmemBytesB = kOffTmemB + 16 + 1024;
+static_assert(kSmemBytesB <= 232448, "shared memory budget exceeded");
+
+struct BwdMaps {
+  CUtensorMap w, in, out[kNLb];
+};
+struct BwdArgs {
+  int64_t M;
+  int num_tiles;
+  const float* d_ssig;
+  const float* sig_w;
+  const uint32_t* relu_mask;
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sIn = smem + kOffIn;
+  uint8_t* sAct = smem + kOffActB;
+  uint8_t* sW = smem + kOffWB;
+  float* sSigW = reinterpret_cast<float*>(smem + kOffSigW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarB);
+  uint64_t* bar_wfull = bars;
+  uint64_t* bar_wempty = bars + kWStages;
+  uint64_t* bar_infull = bars + 2 * kWStages;
+  uint64_t* bar_inempty = bars + 2 * kWStages + 1;
+  uint64_t* bar_act = bars + 2 * kWStages + 2;
+  uint64_t* bar_tfull = bars + 2 * kWStages + 6;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmemB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit0 = blockIdx.x / kCluster;
+  const int unit_step = gridDim.x / kCluster;
+  const int num_units = (args.num_tiles + kCluster - 1) / kCluster;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCluster) - 1);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.w);
+    prefetch_tmap(&maps.in);
+    for (int i = 0; i < kNLb; ++i) prefetch_tmap(&maps.out[i]);
+    for (int i = 0; i < kWStages; ++i) {
+      mbar_init(&bar_wfull[i], 1);
+      mbar_init(&bar_wempty[i], kCluster);
+    }
+    mbar_init(bar_infull, 1);
+    mbar_init(bar_inempty, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_tfull[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < 256; i += kEpiThreads) sSigW[i] = args.sig_w ? args.sig_w[i] : 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      auto load_w = [&](int kcol) {
+        mbar_wait(&bar_wempty[ws], wph ^ 1);
+        mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
+        if (kCluster == 1) {
+          tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
+        } else {
+          constexpr int kPart = kWBytes / kCluster;
+          tma_load_2d_mc(sW + ws * kWBytes + cta_rank * kPart, &maps.w, &bar_wfull[ws], kcol,
+                         cta_rank * (256 / kCluster), kMask);
+        }
+        if (++ws == kWStages) {
+          ws = 0;
+          wph ^= 1;
+        }
+      };
+      auto load_in = [&](int t, int tile) {
+        mbar_wait(bar_inempty, (t & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_infull, kActBytes);
+        for (int b = 0; b < 4; ++b)
+          tma_load_2d(sIn + b * kBoxBytes, &maps.in, bar_infull, b * 64, tile * kTileM);
+      };
+      int t = 0;
+      if (unit0 < num_units) load_in(0, unit0 * kCluster + cta_rank);
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
+        for (int j = 0; j < kNLb; ++j) {
+          for (int b = 0; b < 4; ++b) load_w(j * 256 + b * 64);
+          if (j == 1) {  // layer 0's MMAs have retired by now: its input buffer is free
+            const int next = unit + unit_step;
+            if (next < num_units) load_in(t + 1, next * kCluster + cta_rank);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
+      int ws = 0;
+      uint32_t wph = 0;
+      uint32_t act_ph = 0;
+      uint32_t g = 0;
+      int t = 0;
+      auto free_stage = [&](uint64_t* bar) {
+        if (kCluster == 1) mma_commit(bar);
+        else mma_commit_mc(bar, kMask);
+      };
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
+        for (int j = 0; j < kNLb; ++j, ++g) {
+          const uint32_t d_tmem = tmem_base + (g & 1) * 256;
+          uint32_t accum = 0;
+          if (j == 0) mbar_wait(bar_infull, t & 1);
+#pragma unroll 1
+          for (int b = 0; b < 4; ++b) {
+            mbar_wait(&bar_wfull[ws], wph);
+            if (j > 0) mbar_wait(&bar_act[b], act_ph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32((j == 0 ? sIn : sAct) + b * kBoxBytes);
+            const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                          umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
+              accum = 1;
+            }
+            free_stage(&bar_wempty[ws]);
+            if (++ws == kWStages) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+          if (j == 0) mma_commit(bar_inempty);
+          else act_ph ^= 1;
+          mma_commit(&bar_tfull[g & 1]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (see forward)
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
+    const int half = grp & 1;
+    const int set = grp >> 1;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const bool lane0 = lane_id() == 0;
+    const bool leader = ((ew & 7) == 0) && lane0;
+    const uint32_t set_bar = 2 + set;
+    const uint32_t sact_row = smem_u32(sAct) + row * 128;
+    const uint32_t ssigw = smem_u32(sSigW);
+    const uint32_t swz = row & 7;
+    uint32_t g = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step) {
+      const int tile = unit * kCluster + cta_rank;
+      const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
+      const bool in_range = tile < args.num_tiles;
+      const float ds = (args.d_ssig && grow < args.M) ? args.d_ssig[grow] : 0.f;
+      for (int j = 0; j < kNLb; ++j, ++g) {
+        // ReLU mask words of H(8-j) for my two chunks (forward layer index 7-j); issued before the
+        // accumulator wait so the loads are long done when they are needed
+        const uint32_t* mrow =
+            args.relu_mask + ((static_cast<int64_t>(in_range ? tile : 0) * 8 + (7 - j)) * 8) * kTileM + row;
+        const uint32_t mA = __ldg(mrow + (set * 2 + half) * kTileM);
+        const uint32_t mB = __ldg(mrow + ((set + 2) * 2 + half) * kTileM);
+        mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
+        uint32_t r[2][16];
+        tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int box = set + (q & 2);
+          const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+          tmem_ld_wait_dep(r[q & 1]);
+          if (q < 3) {
+            const int nbox = set + ((q + 1) & 2);
+            tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
+          }
+          const uint32_t* rr = r[q & 1];
+          const uint32_t m16 = ((q & 2) ? mB : mA) >> ((q & 1) * 16);
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
+          if (j == 0) {
+            // + d_ssig (x) w_sigma : the share_sigma head hangs off H8 (models/nerf.py:89)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 w4 = lds128(ssigw + (col0 + k * 4) * 4);
+              v[k * 4 + 0] += ds * w4.x;
+              v[k * 4 + 1] += ds * w4.y;
+              v[k * 4 + 2] += ds * w4.z;
+              v[k * 4 + 3] += ds * w4.w;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = ((m16 >> e) & 1u) ? v[e] : 0.f;
+          uint4 o[2];
+          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          const uint32_t box_row = sact_row + box * kBoxBytes;
+          const uint32_t s0 = half * 4 + (q & 1) * 2;
+          sts128(box_row + ((s0 ^ swz) << 4), o[0]);
+          sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
+          if (q & 1) {
+            fence_proxy_async_smem();
+            if (j < kNLb - 1) {
+              tc_fence_before_sync();
+              __syncwarp();
+              if (lane0) mbar_arrive(&bar_act[box]);
+            }
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(set_bar, kSetThreads);
+            if (leader) {
+              tma_store_2d(&maps.out[j], sAct + box * kBoxBytes, box * 64, tile * kTileM);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (kCluster > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace bwd
 
 // 2 (default): CTA pairs share the weight stream by TMA multicast; UPNERF_TRUNK_CLUSTER=1
 // selects independent CTAs (for A/B measurements).
@@ -418,6 +700,7 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   args.head_w = a->sigma_w;
   args.head_b = a->sigma_b;
   args.head_out = a->s_sigma;
+  args.relu_mask = a->relu_mask;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -452,5 +735,70 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
   }
   UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_kernel");
+  return UPNERF_OK;
+}
+
+extern "C" int64_t upnerf_trunk_mask_words(int64_t M) {
+  return upnerf::ceil_div64(M, upnerf::kTileM) * 8 * 8 * upnerf::kTileM;
+}
+
+extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* stream) {
+  using namespace upnerf;
+  using namespace upnerf::bwd;
+  UPNERF_REQUIRE(a && a->M > 0, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: M=%lld", a ? (long long)a->M : -1ll);
+  UPNERF_REQUIRE(a->d_hf && a->wcat_t && a->relu_mask && a->sigma_w, UPNERF_ERR_BAD_SHAPE,
+                 "mlp_trunk_bwd: missing operand");
+  UPNERF_REQUIRE(a->ld_w >= UPNERF_TRUNK_WCATT_COLS, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: ld_w=%lld < %d",
+                 (long long)a->ld_w, UPNERF_TRUNK_WCATT_COLS);
+  const int64_t tiles = ceil_div64(a->M, kTileM);
+  UPNERF_REQUIRE(tiles < (1ll << 24), UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: M too large");
+  BwdMaps maps;
+  BwdArgs args;
+  memset(&args, 0, sizeof(args));
+  args.M = a->M;
+  args.num_tiles = static_cast<int>(tiles);
+  args.d_ssig = a->d_ssig;
+  args.sig_w = a->sigma_w;
+  args.relu_mask = a->relu_mask;
+  const int cluster = trunk_cluster_size();
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 256 / cluster, 64));
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.in, a->d_hf, a->M, 256, a->ld_dhf, kTileM, 64));
+  for (int j = 0; j < kNLb; ++j) {
+    UPNERF_REQUIRE(a->d_out[j], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: d_out[%d] missing", j);
+    UPNERF_TRY(make_tmap_bf16_2d(&maps.out[j], a->d_out[j], a->M, 256, a->ld_dout[j], kTileM, 64));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytesB));
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytesB));
+    attr_set = true;
+  }
+  const double flop = 2.0 * a->M * 256.0 * 256.0 * kNLb;
+  LaunchScope scope(kCatGemmTc, as_stream(stream), flop);
+  if (cluster == 1) {
+    const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+    mlp_trunk_bwd_kernel<1><<<grid, kThreads, kSmemBytesB, as_stream(stream)>>>(maps, args);
+  } else {
+    const int64_t units = ceil_div64(tiles, 2);
+    const int max_clusters = sm_count() / 2;
+    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytesB;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_bwd_kernel<2>, maps, args));
+  }
+  UPNERF_CHECK_LAUNCH("mlp_trunk_bwd_kernel");
   return UPNERF_OK;
 }

@@ -90,12 +90,16 @@ struct Bump {
   void* take_bytes(uint64_t bytes) { return take<uint8_t>(bytes); }
 };
 
-constexpr int WCAT = UPNERF_TRUNK_WCAT_COLS;  // trunk forward weights, concatenated along K
+constexpr int WCAT = UPNERF_TRUNK_WCAT_COLS;    // trunk forward weights, concatenated along K
+constexpr int WCATT = UPNERF_TRUNK_WCATT_COLS;  // transposed trunk weights in backward-chain order
 struct Packed {  // GEMM operands derived from the fp32 parameters (element type T)
   void* Wcat;                                           // [256, WCAT]: W1|W2|W3|W4|W5=[h|PE]|W6|W7|W8|WF
   void *W1, *Wk[8], *W5, *WF;                           // views into Wcat (row stride WCAT)
   void *Wc1, *Wc2, *Wq;                                 // [N, K] K-major
-  void *W1T, *WkT[8], *W5T, *WFT, *Wc1T, *Wc2T, *WqT;  // transposed for the data gradient
+  void* WcatT;                                          // [256, WCATT]: WF^T|W8^T|W7^T|W6^T|W5h^T|W4^T|W3^T|W2^T
+  void *WkT[8], *W5T, *WFT;                             // views into WcatT (row stride WCATT); W5T = h part
+  void *W1T, *W5peT;                                    // [64, 256]: rows = PE columns (for dPE)
+  void *Wc1T, *Wc2T, *WqT;                              // transposed for the data gradient
   float* Wq32;      // [128,256] fp32 folded rgb weight
   float* bq_const;  // [128]
   float* band_xyz;  // [16]
@@ -110,12 +114,13 @@ struct PassBufs {
   // saved by forward
   void *X4, *Hs[9], *HF, *G1, *G2, *Q;  // Hs[1..8]; Hs[4] aliases X4 (ld 320)
   float *ssig, *csig, *rgb, *z;
+  uint32_t* relu_mask;  // bit masks of H1..H8 (bf16 mode: written by the fused forward)
   float *HFr, *G2r, *Wsum, *Wcsum, *P, *Crows, *Bq, *Bc;
   Packed pk;
 };
 
 struct Scratch {
-  void *dA, *dB, *dHF, *dG2p, *dG1p, *dQp, *dPE;
+  void *dY[8], *dHF, *dG2p, *dG1p, *dQp, *dPE;  // dY[j] = gradient of layer (8-j)'s pre-activation
   float *dssig, *dcsig, *drgb;
   float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
 };
@@ -134,6 +139,7 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBu
   p->csig = b.take<float>(M);
   p->rgb = b.take<float>(M * 3);
   p->z = b.take<float>(M);
+  p->relu_mask = b.take<uint32_t>(es == 2 ? upnerf_trunk_mask_words(M) : 0);
   p->HFr = b.take<float>(R * W);
   p->G2r = b.take<float>(R * H);
   p->Wsum = b.take<float>(R);
@@ -167,14 +173,23 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBu
     }
     k.WF = view(W);
   }
-  k.W1T = b.take_bytes(PEW * W * es);
-  for (int i = 0; i < 8; ++i) {
-    k.WkT[i] = nullptr;
-    if (i == 0 || i == 4) continue;
-    k.WkT[i] = b.take_bytes(W * W * es);
+  k.WcatT = b.take_bytes(static_cast<uint64_t>(W) * WCATT * es);
+  {
+    int64_t c = 0;
+    auto view = [&]() {
+      void* p = k.WcatT ? static_cast<uint8_t*>(k.WcatT) + c * es : nullptr;
+      c += W;
+      return p;
+    };
+    k.WFT = view();
+    for (int i = 7; i >= 1; --i) {
+      if (i == 4) k.W5T = view();
+      else k.WkT[i] = view();
+    }
+    k.WkT[0] = k.WkT[4] = nullptr;
   }
-  k.W5T = b.take_bytes(X4W * W * es);
-  k.WFT = b.take_bytes(W * W * es);
+  k.W1T = b.take_bytes(PEW * W * es);
+  k.W5peT = b.take_bytes(PEW * W * es);
   k.Wc1 = b.take_bytes(H * W * es);
   k.Wc1T = b.take_bytes(W * H * es);
   k.Wc2 = b.take_bytes(H * H * es);
@@ -186,8 +201,9 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBu
 
 void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scratch* s) {
   const int64_t M = R * S;
-  s->dA = b.take_bytes(M * W * es);
-  s->dB = b.take_bytes(M * W * es);
+  // bf16 mode keeps all eight (the fused chain writes them, the weight gradients read them);
+  // fp32 mode ping-pongs two
+  for (int j = 0; j < 8; ++j) s->dY[j] = (es == 2 || j < 2) ? b.take_bytes(M * W * es) : nullptr;
   s->dHF = b.take_bytes(M * W * es);
   s->dG2p = b.take_bytes(M * H * es);
   s->dG1p = b.take_bytes(M * H * es);
@@ -344,15 +360,15 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
   for (int i = 1; i < 8; ++i) {
     if (i == 4) continue;
     add(prm + L.Wl[i], W, k.Wk[i], WCAT, W, W, 0);
-    add(prm + L.Wl[i], W, k.WkT[i], W, W, W, 1);
+    add(prm + L.Wl[i], W, k.WkT[i], WCATT, W, W, 1);
   }
   // skip layer: reference input is [PE | h]; the packed input is [h | PE | 0]
   add(prm + L.Wl[4] + ix, W + ix, k.W5, WCAT, W, W, 0);
   add(prm + L.Wl[4], W + ix, col(k.W5, W, c.es), WCAT, W, ix, 0);
-  add(prm + L.Wl[4] + ix, W + ix, k.W5T, W, W, W, 1);
-  add(prm + L.Wl[4], W + ix, col(k.W5T, static_cast<int64_t>(W) * W, c.es), W, W, ix, 1);
+  add(prm + L.Wl[4] + ix, W + ix, k.W5T, WCATT, W, W, 1);
+  add(prm + L.Wl[4], W + ix, k.W5peT, W, W, ix, 1);
   add(prm + L.Wf, W, k.WF, WCAT, W, W, 0);
-  add(prm + L.Wf, W, k.WFT, W, W, W, 1);
+  add(prm + L.Wf, W, k.WFT, WCATT, W, W, 1);
   if (ph.cand) {
     add(prm + L.Wc0, W + L.cd, k.Wc1, W, H, W, 0);
     add(prm + L.Wc0, W + L.cd, k.Wc1T, H, H, W, 1);
@@ -410,6 +426,7 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     ta.sigma_w = prm + L.Ws; ta.sigma_b = prm + L.bs;
     ta.s_sigma = p.ssig;
     ta.M = M;
+    ta.relu_mask = p.relu_mask;
     UPNERF_TRY(upnerf_mlp_trunk_fwd_bf16(&ta, c.st));
   } else {
     e.act = 1;
@@ -624,33 +641,50 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // 5. xyz_encoding_final + share_sigma  ->  dH8_pre
   UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, c.st));
-  void* dcur = s.dA;
-  void* dnext = s.dB;
-  if (dhf_live) {
+  UPNERF_REQUIRE(dhf_live, UPNERF_ERR_BAD_CONFIG, "backward without any gradient into xyz_encoding_final");
+  {
     const Seg sgW{0, W, 0};
     UPNERF_TRY(wgrad(c, s.dHF, W, p.Hs[8], W, g + L.Wf, W, g + L.bf, M, W, W, &sgW, 1));
+  }
+  const void* PE = col(p.X4, W, c.es);
+  const bool fused = c.dtype == UPNERF_BF16;
+  if (fused) {
+    // the whole data-gradient chain dHF -> dY8 .. dY1 in one persistent tcgen05 kernel
+    upnerf_trunk_bwd_args ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.d_hf = s.dHF; ba.ld_dhf = W;
+    ba.d_ssig = s.dssig; ba.sigma_w = prm + L.Ws;
+    ba.wcat_t = k.WcatT; ba.ld_w = WCATT;
+    ba.relu_mask = p.relu_mask;
+    for (int j = 0; j < 8; ++j) { ba.d_out[j] = s.dY[j]; ba.ld_dout[j] = W; }
+    ba.M = M;
+    UPNERF_TRY(upnerf_mlp_trunk_bwd_bf16(&ba, c.st));
+  } else {
     e = ep_none();
     e.rank1_row = s.dssig; e.rank1_col = prm + L.Ws;
     e.aux = p.Hs[8]; e.ldaux = W; e.aux_mode = 2;
-    UPNERF_TRY(linear(c, s.dHF, W, k.WFT, W, dcur, W, M, W, W, e));
-  } else {
-    UPNERF_REQUIRE(false, UPNERF_ERR_BAD_CONFIG, "backward without any gradient into xyz_encoding_final");
+    UPNERF_TRY(linear(c, s.dHF, W, k.WFT, WCATT, s.dY[0], W, M, W, W, e));
   }
 
-  // 6. trunk, layers 8..1
-  const void* PE = col(p.X4, W, c.es);
+  // 6. trunk, layers 8..1: weight gradients (and, layer-wise mode, the data gradients)
   bool dpe_live = false;
   for (int i = 7; i >= 0; --i) {
     // dcur = dH_{i+1}_pre ; input of layer i+1 is Hs[i] (or PE for i == 0, X4 for i == 4)
+    void* dcur = fused ? s.dY[7 - i] : s.dY[(7 - i) & 1];
+    void* dnext = fused ? nullptr : s.dY[(8 - i) & 1];
     if (i == 4) {
       const Seg sg[2] = {{0, W, L.in_xyz}, {W, L.in_xyz, 0}};
       UPNERF_TRY(wgrad(c, dcur, W, p.X4, X4W, g + L.Wl[4], W + L.in_xyz, g + L.bl[4], M, W, X4W, sg, 2));
-      e = ep_none();
-      e.aux = p.X4; e.ldaux = X4W; e.aux_mode = 2;
-      UPNERF_TRY(linear(c, dcur, W, k.W5T, W, dnext, W, M, W, W, e));
-      e = ep_none();
-      UPNERF_TRY(linear(c, dcur, W, col(k.W5T, static_cast<int64_t>(W) * W, c.es), W, s.dPE, PEW, M, PEW, W, e));
-      dpe_live = true;
+      if (!fused) {
+        e = ep_none();
+        e.aux = p.X4; e.ldaux = X4W; e.aux_mode = 2;
+        UPNERF_TRY(linear(c, dcur, W, k.W5T, WCATT, dnext, W, M, W, W, e));
+      }
+      if (a.d_rays) {
+        e = ep_none();
+        UPNERF_TRY(linear(c, dcur, W, k.W5peT, W, s.dPE, PEW, M, PEW, W, e));
+        dpe_live = true;
+      }
     } else if (i == 0) {
       const Seg sg{0, L.in_xyz, 0};
       UPNERF_TRY(wgrad(c, dcur, W, PE, X4W, g + L.Wl[0], L.in_xyz, g + L.bl[0], M, W, PEW, &sg, 1));
@@ -659,16 +693,15 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
         if (dpe_live) { e.aux = s.dPE; e.ldaux = PEW; e.aux_mode = 1; }
         UPNERF_TRY(linear(c, dcur, W, k.W1T, W, s.dPE, PEW, M, PEW, W, e));
       }
-      break;
     } else {
-      const int64_t ldin = (i == 4) ? X4W : W;
       const Seg sg{0, W, 0};
-      UPNERF_TRY(wgrad(c, dcur, W, p.Hs[i], ldin, g + L.Wl[i], W, g + L.bl[i], M, W, W, &sg, 1));
-      e = ep_none();
-      e.aux = p.Hs[i]; e.ldaux = ldin; e.aux_mode = 2;
-      UPNERF_TRY(linear(c, dcur, W, k.WkT[i], W, dnext, W, M, W, W, e));
+      UPNERF_TRY(wgrad(c, dcur, W, p.Hs[i], W, g + L.Wl[i], W, g + L.bl[i], M, W, W, &sg, 1));
+      if (!fused) {
+        e = ep_none();
+        e.aux = p.Hs[i]; e.ldaux = W; e.aux_mode = 2;
+        UPNERF_TRY(linear(c, dcur, W, k.WkT[i], WCATT, dnext, W, M, W, W, e));
+      }
     }
-    void* t = dcur; dcur = dnext; dnext = t;
   }
 
   // 7. positional encoding backward -> ray gradients
