@@ -35,7 +35,8 @@ S_C, N_IMP = 64, 64
 PROGRESS = 0.30                  # phase 1 (sched_mult = 0.5): the superset of work, headline phase
 MACS = {0: 755_584, 1: 814_720, 2: 714_240}     # per-sample MACs of the reference MLP
 FLOP_PER_RAY = (S_C + S_C + N_IMP) * MACS[1] * 2 * 3
-CATS = ["gemm_tc", "wgrad_tc", "gemm_simt", "composite", "posenc", "sampling", "pose_rays", "heads", "pack"]
+CATS = ["gemm_tc", "wgrad_tc", "gemm_simt", "composite", "posenc", "sampling", "pose_rays", "heads", "pack",
+        "trunk_fwd", "trunk_bwd"]
 
 
 def peaks():
@@ -48,9 +49,23 @@ def peaks():
 
 
 def host_batch(R, seed, pinned):
-    from oracle import synth
-
-    b = synth.ray_batch(R, N_IMG, seed, random_pose=False)     # poses start at identity (pose.noise = -1)
+    """One synthetic training batch in the reference's layout (datasets/phototourism.py:420-454,
+    SURVEY.md 8(a0)): random pixels of 512x384 / f=400 cameras, random image ids, identity poses
+    (pose.noise = -1), U[0,1) colours, unit-norm 384-d features, inverse depths in [1/far, 1/near]."""
+    g = torch.Generator().manual_seed(seed)
+    near, far = 0.1, 5.0
+    px = torch.randint(0, 512, (R,), generator=g).float()
+    py = torch.randint(0, 384, (R,), generator=g).float()
+    feats = torch.nn.functional.normalize(torch.randn(R, 384, generator=g), dim=-1)
+    b = {
+        "ray_infos": torch.tensor([[near, far]]).repeat(R, 1),
+        "directions": torch.stack([(px - 256) / 400.0, -(py - 192) / 400.0, -torch.ones(R)], -1),
+        "c2w": torch.eye(3, 4).expand(R, 3, 4).contiguous(),
+        "rgbs": torch.rand(R, 3, generator=g),
+        "feats": feats,
+        "img_idx": torch.randint(0, N_IMG, (R,), generator=g),
+        "inv_depths": 1 / far + (1 / near - 1 / far) * torch.rand(R, generator=g),
+    }
     if pinned:
         b = {k: v.pin_memory() for k, v in b.items()}
     return b
@@ -77,7 +92,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -135,14 +150,17 @@ def cpu_port_rate(R_sample, steps, warmup, threads):
 
 
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the step (oracle port: the Python
+    reference cannot travel to the GPU box), all host threads, bounded number of full batches."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    R_sample = 512
-    rate, sec = cpu_port_rate(R_sample, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)), threads)
-    sample = (f"{R_sample} rays/step of the same train step (64+64 samples, phase 1, {N_IMG} images), oracle port, "
-              f"{threads} torch threads, flush-denormal on")
+    R_sample = args.rays
+    n_steps, n_warm = max(1, min(args.steps, 3)), 1
+    rate, sec = cpu_port_rate(R_sample, n_steps, n_warm, threads)
+    sample = (f"{n_steps} timed + {n_warm} warm-up steps of {R_sample} rays of the same train step (64+64 samples, phase 1, "
+              f"{N_IMG} images), oracle port, {threads} torch threads, flush-denormal on")
     line = {
         "impl": "reference", "metric": "train rays/s (fwd+bwd, 64+64 samp/ray)", "value": rate, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
@@ -154,18 +172,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes measured by `ncu --set full` for `kernel` (profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from the committed captures): (sum dram bytes, sum algorithmic bytes, source)."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text()).get(kernel)
+    if not d:
+        return None
+    return sum(x["dram_bytes"] for x in d["launches"]), sum(x["algorithmic_bytes"] for x in d["launches"]), d["source"]
+
+
 def workload_config(args, precision):
     return {"workload": "BASELINE config 2+3: full UP-NeRF train step (pose refinement + coarse/fine render with "
                         "sample_pdf + embeddings + TransientNet/beta loss + backward + 2x Adam), phase 1 (sched_mult 0.5)",
             "rays_per_gpu": args.rays, "n_samples": S_C, "n_importance": N_IMP, "n_images": N_IMG,
             "precision": precision, "parallelism": f"ray-sharded dp{args.gpus}",
-            "l2_policy": "activations per step (>5 GB) exceed the 126 MB L2; no explicit flush"}
+            "l2_policy": "inputs larger than L2: every step streams >5 GB of activations through the 126 MB L2; "
+                         "no explicit flush"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=4096, help="rays per GPU per step")
@@ -261,12 +292,12 @@ def main():
             system.training_step(dev_batches[i % n_batches], i)
         torch.cuda.synchronize()
         n = len(CATS)
-        ms_a, ln_a, wk_a = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)()
-        L.check(lib.upnerf_profile_collect(ms_a, ln_a, wk_a, n), "upnerf_profile_collect")
+        ms_a, ln_a, wk_a, by_a = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)(), (C.c_double * n)()
+        L.check(lib.upnerf_profile_collect(ms_a, ln_a, wk_a, by_a, n), "upnerf_profile_collect")
         lib.upnerf_profile_enable(0)
         for i, c in enumerate(CATS):
             prof[c] = {"ms_per_step": ms_a[i] / n_prof, "launches_per_step": ln_a[i] / n_prof,
-                       "work_per_step": wk_a[i] / n_prof}
+                       "work_per_step": wk_a[i] / n_prof, "bytes_per_step": by_a[i] / n_prof}
     if world > 1:
         dist.barrier()
 
@@ -275,17 +306,43 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
-    tc_ms = prof["gemm_tc"]["ms_per_step"] + prof["wgrad_tc"]["ms_per_step"]
-    tc_flop = prof["gemm_tc"]["work_per_step"] + prof["wgrad_tc"]["work_per_step"]
-    n_tc = prof["gemm_tc"]["launches_per_step"] + prof["wgrad_tc"]["launches_per_step"]
-    achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel + wgrad_tc_kernel (tcgen05 dense layers)",
-        "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-        "peak_source": f"{pk['source']} bf16_tflops_sustained (kernels timed inside a long step)",
-        "flop_per_launch_avg": tc_flop / max(n_tc, 1), "ms_per_launch_avg": tc_ms / max(n_tc, 1),
-        "share_of_step": tc_ms / sum(p["ms_per_step"] for p in prof.values()),
-        "traffic": None,
+    fam_total = sum(p["ms_per_step"] for p in prof.values())
+
+    def hbm_view(cat, kernel):
+        p = prof[cat]
+        n = max(p["launches_per_step"], 1)
+        gbs = p["bytes_per_step"] / (p["ms_per_step"] * 1e-3) / 1e9 if p["ms_per_step"] > 0 else 0.0
+        r = {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+             "frac": gbs / pk["hbm_gbs"], "peak_source": f"{pk['source']} hbm_gbs (copy bandwidth)",
+             "algorithmic_bytes_per_launch": p["bytes_per_step"] / n, "ms_per_launch": p["ms_per_step"] / n,
+             "launches_per_step": n, "share_of_step": p["ms_per_step"] / fam_total, "traffic": None}
+        t = ncu_traffic(kernel)
+        if t:   # measured DRAM bytes scaled from the profiled launches to this run's average launch
+            r["traffic"] = r["algorithmic_bytes_per_launch"] * t[0] / t[1]
+            r["traffic_source"] = t[2]
+        return r
+
+    def tensor_view(cats, kernel):
+        ms_ = sum(prof[c]["ms_per_step"] for c in cats)
+        fl = sum(prof[c]["work_per_step"] for c in cats)
+        n = max(sum(prof[c]["launches_per_step"] for c in cats), 1)
+        tf = fl / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
+        return {"bound": "tensor", "kernel": kernel, "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": tf / pk["tf_sustained"],
+                "peak_source": f"{pk['source']} bf16_tflops_sustained (kernels timed inside a long step)",
+                "flop_per_launch": fl / n, "ms_per_launch": ms_ / n, "share_of_step": ms_ / fam_total}
+
+    # The kernel with the largest share of the step is the weight-gradient GEMM; it streams both of
+    # its operands from HBM once (128 flop/byte at N = K = 256, below the machine balance of ~220),
+    # so HBM bandwidth bounds it.  The tensor-pipe view of the fused MLP kernels and of all tcgen05
+    # kernels together follows as extra objects.
+    roofline = hbm_view("wgrad_tc", "wgrad_tc_kernel")
+    all_tc = ["gemm_tc", "wgrad_tc", "trunk_fwd", "trunk_bwd"]
+    roofline_mlp = {
+        "fused_trunk": tensor_view(["trunk_fwd", "trunk_bwd"], "mlp_trunk_fwd_kernel + mlp_trunk_bwd_kernel"),
+        "fused_trunk_hbm": {c: hbm_view(c, k) for c, k in (("trunk_fwd", "mlp_trunk_fwd_kernel"),
+                                                            ("trunk_bwd", "mlp_trunk_bwd_kernel"))},
+        "all_tcgen05": tensor_view(all_tc, "all tcgen05 kernels (fused trunk, layer GEMMs, weight gradients)"),
         "whole_step_algorithmic": {"flop_per_ray": FLOP_PER_RAY, "tflops": value / world * FLOP_PER_RAY / 1e12,
                                    "frac_of_sustained_peak": value / world * FLOP_PER_RAY / 1e12 / pk["tf_sustained"]},
         "families_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in prof.items()},
@@ -300,13 +357,14 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
+        "roofline_mlp": roofline_mlp,
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, sec = cpu_port_rate(256, 2, 1, threads)
+        rate, sec = cpu_port_rate(2048, 4, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-                                "sample": f"256 rays/step x 2 steps of the same train step (oracle port, {threads} torch "
-                                          f"threads, flush-denormal on), {sec:.2f} s/step"}
+                                "sample": f"2048 rays/step x 4 timed steps (+1 warm-up) of the same train step (oracle port, "
+                                          f"{threads} torch threads, flush-denormal on), {sec:.2f} s/step"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -46,10 +46,12 @@ int upnerf_device_ok(void);
 /* Launch accounting for bench.py: total kernels launched by this library in the process,
  * and (while enabled) CUDA-event device time / launches / declared work per kernel family:
  * 0 gemm_tc, 1 wgrad_tc, 2 gemm_simt, 3 composite, 4 posenc, 5 sampling, 6 pose_rays,
- * 7 heads, 8 pack.  work = 2*M*N*K flop for the GEMM families, 0 otherwise. */
+ * 7 heads, 8 pack, 9 trunk_fwd (fused), 10 trunk_bwd (fused).  work = flop of the launch
+ * (2*M*N*K per GEMM), bytes = its algorithmic memory traffic (every operand touched once);
+ * both 0 for families that do not declare them. */
 long long upnerf_launch_count(void);
 void upnerf_profile_enable(int on);
-int upnerf_profile_collect(double* ms, long long* launches, double* work, int ncat);
+int upnerf_profile_collect(double* ms, long long* launches, double* work, double* bytes, int ncat);
 
 /* ------------------------------------------------------------------------------------
  * Dense layer primitive (the "one dense contraction" of the path).
@@ -92,7 +94,8 @@ int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, voi
  *   pe    [M, 64]  bf16, row stride ld_pe (the 63-wide encoding, zero padded)
  *   wcat  [256, UPNERF_TRUNK_WCAT_COLS] bf16 K-major, row stride ld_w, columns
  *         [W1 (64) | W2 | W3 | W4 | W5 as [h (256) | PE (64)] | W6 | W7 | W8 | W_final]
- *   bias[l] [256] fp32; out[l] [M,256] bf16 row stride ld_out[l] (l = 0..7: H1..H8, 8: final)
+ *   bias[l] [256] fp32; out[l] [M,256] bf16 row stride ld_out[l] (l = 0..7: H1..H8, 8: final);
+ *   out[l] == NULL skips that store (inference keeps only the final output)
  *   s_sigma [M] fp32 = Softplus(H8 . sigma_w + sigma_b) */
 #define UPNERF_TRUNK_LAYERS 9
 #define UPNERF_TRUNK_WCAT_COLS 2176
@@ -348,6 +351,8 @@ typedef struct upnerf_render_args {
   float* d_rays;             /* backward output [R,8], accumulated, or NULL */
   void* workspace;           /* activations saved by forward for backward + scratch */
   uint64_t workspace_bytes;
+  int no_grad;               /* 1: forward only (inference): activations are not kept, the
+                                workspace is ~4x smaller and upnerf_render_bwd is refused */
 } upnerf_render_args;
 
 int64_t upnerf_nerf_param_count(const upnerf_net_config* cfg);

@@ -237,3 +237,30 @@ def test_nerf_forward_per_sample_api_golden(cuda_dev, name):
         pe = mod.positional_encoding(inputs["input_xyz"], cfg.xyz_L).cpu()
         ref_pe = O.positional_encoding(g["xyz"], cfg.xyz_L, prog, cfg.c2f)
         assert float((pe - ref_pe).abs().max()) <= 1e-5      # same fp32 argument x*f_k, full-accuracy sincosf
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_inference_render_no_grad_matches_training_forward(cuda_dev, precision):
+    """Config 5 path (validation / tto render: perturb=0, deterministic sample_pdf, sched_mult=1, under
+    torch.no_grad, chunked by the caller like models/nerf_system.py:104-126).  The forward-only mode keeps
+    no activations; its outputs must equal the training-mode forward bit for bit, chunk by chunk."""
+    from upnerf_b200.models.rendering import render_rays
+
+    kw, _ = NET_CASES["full"]
+    R, S, NI, n_img, chunk = 640, 64, 64, 31, 256
+    _, _, models, _, embs = build_modules(kw, 23, 0.75, cuda_dev, n_img, emb_seed=9)
+    b = synth.ray_batch(R, n_img, 35)
+    o, d = O.get_rays(b["directions"], b["c2w"])
+    rays = torch.cat([o, d, b["ray_infos"]], 1).to(cuda_dev)
+    idx = b["img_idx"].to(cuda_dev)
+    kwargs = dict(models=models, embeddings=embs, sched_mult=1.0, N_samples=S, perturb=0, N_importance=NI,
+                  encode_feat=True, precision=precision)
+    full = render_rays(rays=rays.clone().requires_grad_(True), img_idx=idx, **kwargs)
+    assert set(full) == {"s_weights_coarse", "s_rgb_coarse", "s_depth_coarse", "s_weights_fine", "s_rgb_fine", "s_depth_fine"}
+    with torch.no_grad():
+        parts = [render_rays(rays=rays[i:i + chunk], img_idx=idx[i:i + chunk], **kwargs) for i in range(0, R, chunk)]
+    for k, v in full.items():
+        got = torch.cat([p[k] for p in parts], 0)
+        assert not got.requires_grad
+        assert torch.equal(got, v.detach()), k
+    assert float(full["s_rgb_fine"].min()) >= 0 and float(full["s_rgb_fine"].max()) <= 1

@@ -61,6 +61,18 @@ def main():
     fl = 2.0 * M * 256 * sum(ks)
     by = (M * 64 + 9 * M * 256) * 2
     print(f"mlp_trunk_fwd M={M}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s (write-only activations)")
+    mask = torch.zeros(L.trunk_mask_words(M), dtype=torch.int32, device=dev)
+    L.mlp_trunk_fwd(pe, wcat, bs, sw, sb, outs, sig, M, relu_mask=mask)
+    ms = timeit(lambda: L.mlp_trunk_fwd(pe, wcat, bs, sw, sb, outs, sig, M, relu_mask=mask))
+    print(f"mlp_trunk_fwd (+mask) M={M}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    wcat_t = (torch.randn(256, 2048, device=dev) / 16).bfloat16()
+    d_hf = torch.randn(M, 256, device=dev).bfloat16()
+    d_ssig = torch.randn(M, device=dev)
+    d_outs = [torch.empty(M, 256, device=dev, dtype=torch.bfloat16) for _ in range(8)]
+    ms = timeit(lambda: L.mlp_trunk_bwd(d_hf, d_ssig, sw, wcat_t, mask, d_outs, M))
+    fl = 2.0 * M * 256 * 2048
+    by = (M * 256 + 8 * M * 256) * 2 + mask.numel() * 4
+    print(f"mlp_trunk_bwd M={M}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
     if only_trunk:
         return
     Mf = 256 * 192

@@ -73,12 +73,13 @@ struct Prof {
   bool made[kMaxProf] = {};
   int cat[kMaxProf];
   double work[kMaxProf];
+  double bytes[kMaxProf];
 };
 Prof g_prof;
 long long g_launches = 0;
 }  // namespace
 
-LaunchScope::LaunchScope(int cat, cudaStream_t stream, double work) : slot(-1), st(stream) {
+LaunchScope::LaunchScope(int cat, cudaStream_t stream, double work, double bytes) : slot(-1), st(stream) {
   ++g_launches;
   if (!g_prof.enabled || g_prof.n >= kMaxProf) return;
   slot = g_prof.n++;
@@ -89,6 +90,7 @@ LaunchScope::LaunchScope(int cat, cudaStream_t stream, double work) : slot(-1), 
   }
   g_prof.cat[slot] = cat;
   g_prof.work[slot] = work;
+  g_prof.bytes[slot] = bytes;
   cudaEventRecord(g_prof.beg[slot], st);
 }
 LaunchScope::~LaunchScope() {
@@ -106,14 +108,15 @@ void upnerf_profile_enable(int on) {
   upnerf::g_prof.n = 0;
 }
 
-// Sums event-measured device time (ms), launch counts and declared work (flop or bytes) per
+// Sums event-measured device time (ms), launch counts, declared flop and algorithmic bytes per
 // kernel family since upnerf_profile_enable(1); synchronises on the recorded events.
-int upnerf_profile_collect(double* ms, long long* launches, double* work, int ncat) {
+int upnerf_profile_collect(double* ms, long long* launches, double* work, double* bytes, int ncat) {
   using namespace upnerf;
   for (int i = 0; i < ncat; ++i) {
     ms[i] = 0;
     launches[i] = 0;
     work[i] = 0;
+    bytes[i] = 0;
   }
   for (int i = 0; i < g_prof.n; ++i) {
     if (cudaEventSynchronize(g_prof.end[i]) != cudaSuccess) return UPNERF_ERR_CUDA;
@@ -124,6 +127,7 @@ int upnerf_profile_collect(double* ms, long long* launches, double* work, int nc
       ms[c] += t;
       launches[c] += 1;
       work[c] += g_prof.work[i];
+      bytes[c] += g_prof.bytes[i];
     }
   }
   g_prof.n = 0;

@@ -52,12 +52,13 @@ int sm_count();
 // the launching stream so that bench.py can attribute device time to kernel families.
 enum LaunchCat {
   kCatGemmTc = 0, kCatWgradTc, kCatGemmSimt, kCatComposite, kCatPosenc, kCatSampling,
-  kCatPoseRays, kCatHeads, kCatPack, kNumCats
+  kCatPoseRays, kCatHeads, kCatPack, kCatTrunkFwd, kCatTrunkBwd, kNumCats
 };
 struct LaunchScope {
   int slot;
   cudaStream_t st;
-  LaunchScope(int cat, cudaStream_t stream, double work = 0.0);
+  // work = flop of the launch, bytes = its ALGORITHMIC memory traffic (each operand touched once)
+  LaunchScope(int cat, cudaStream_t stream, double work = 0.0, double bytes = 0.0);
   ~LaunchScope();
 };
 

@@ -402,7 +402,8 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
     attr_set = true;
   }
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  LaunchScope scope(kCatGemmTc, as_stream(stream), 2.0 * M * N * K);
+  LaunchScope scope(kCatGemmTc, as_stream(stream), 2.0 * M * N * K,
+                    2.0 * M * (K + N * (args.ep.aux_mode ? 2 : 1)) + 2.0 * N * K);
   gemm_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmA, tmB, tmC, tmAux, args);
   UPNERF_CHECK_LAUNCH("gemm_tc_kernel");
   return UPNERF_OK;

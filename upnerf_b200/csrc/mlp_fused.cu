@@ -65,6 +65,7 @@ struct LayerDesc {
   int feeds;    // output is the A operand of the next layer
   int head;     // share_sigma rides on this layer's epilogue
   int pe_last;  // last user of the PE tile within a sample tile
+  int store;    // keep this layer's output in HBM (backward needs it; inference does not)
 };
 
 struct TrunkMaps {
@@ -287,6 +288,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
       for (int l = 0; l < kNL; ++l, ++g) {
         const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
+        const int store = args.layer[l].store;
         mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
@@ -356,11 +358,13 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             }
             // Box complete once both halves are: store it.  The set's other box is written next;
             // its previous store (the latest group of this leader) must have been read out.
-            if (leader) tma_store_wait_read<0>();
-            named_bar_sync(set_bar, kSetThreads);
-            if (leader) {
-              tma_store_2d(&maps.out[l], sAct + box * kBoxBytes, box * 64, tile * kTileM);
-              tma_store_commit();
+            if (store) {
+              if (leader) tma_store_wait_read<0>();
+              named_bar_sync(set_bar, kSetThreads);
+              if (leader) {
+                tma_store_2d(&maps.out[l], sAct + box * kBoxBytes, box * 64, tile * kTileM);
+                tma_store_commit();
+              }
             }
           }
         }
@@ -667,8 +671,8 @@ int trunk_cluster_size() {
 extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* stream) {
   using namespace upnerf;
   UPNERF_REQUIRE(a && a->M > 0, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: M=%lld", a ? (long long)a->M : -1ll);
-  UPNERF_REQUIRE(a->pe && a->wcat && a->s_sigma && a->sigma_w && a->sigma_b, UPNERF_ERR_BAD_SHAPE,
-                 "mlp_trunk_fwd: missing operand");
+  UPNERF_REQUIRE(a->pe && a->wcat && a->s_sigma && a->sigma_w && a->sigma_b && a->out[kNL - 1],
+                 UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: missing operand");
   UPNERF_REQUIRE(a->ld_w >= UPNERF_TRUNK_WCAT_COLS, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: ld_w=%lld < %d",
                  (long long)a->ld_w, UPNERF_TRUNK_WCAT_COLS);
   const int64_t tiles = ceil_div64(a->M, kTileM);
@@ -686,9 +690,10 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   const int w_act[kNL] = {-1, 64, 320, 576, 832, 1152, 1408, 1664, 1920};
   const int w_pe[kNL] = {0, -1, -1, -1, 1088, -1, -1, -1, -1};
   for (int l = 0; l < kNL; ++l) {
-    UPNERF_REQUIRE(a->out[l], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: out[%d] missing", l);
-    UPNERF_TRY(make_tmap_bf16_2d(&maps.out[l], a->out[l], a->M, 256, a->ld_out[l], kTileM, 64));
     LayerDesc& L = args.layer[l];
+    L.store = a->out[l] != nullptr;
+    if (L.store) UPNERF_TRY(make_tmap_bf16_2d(&maps.out[l], a->out[l], a->M, 256, a->ld_out[l], kTileM, 64));
+    else maps.out[l] = maps.pe;  // never used
     L.w_act = w_act[l];
     L.w_pe = w_pe[l];
     L.relu = l < 8;
@@ -711,7 +716,11 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     attr_set = true;
   }
   const double flop = 2.0 * a->M * 256.0 * (64 + 7 * 256 + 320);
-  LaunchScope scope(kCatGemmTc, as_stream(stream), flop);
+  // algorithmic traffic: read PE, write nine activation tensors + the ReLU bit masks
+  int n_store = 0;
+  for (int l = 0; l < kNL; ++l) n_store += args.layer[l].store;
+  const double bytes = 2.0 * a->M * (64 + n_store * 256) + (a->relu_mask ? 8.0 * 32 * a->M : 0.0);
+  LaunchScope scope(kCatTrunkFwd, as_stream(stream), flop, bytes);
   if (cluster == 1) {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     mlp_trunk_fwd_kernel<1><<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(maps, args);
@@ -776,7 +785,9 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
     attr_set = true;
   }
   const double flop = 2.0 * a->M * 256.0 * 256.0 * kNLb;
-  LaunchScope scope(kCatGemmTc, as_stream(stream), flop);
+  // algorithmic traffic: read dHF + bit masks + d_ssig, write eight gradient tensors
+  const double bytes = 2.0 * a->M * (256 + 8 * 256) + 8.0 * 32 * a->M + 4.0 * a->M;
+  LaunchScope scope(kCatTrunkBwd, as_stream(stream), flop, bytes);
   if (cluster == 1) {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     mlp_trunk_bwd_kernel<1><<<grid, kThreads, kSmemBytesB, as_stream(stream)>>>(maps, args);

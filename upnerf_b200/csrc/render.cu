@@ -125,11 +125,13 @@ struct Scratch {
   float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
 };
 
-void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBufs* p) {
+void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool keep, PassBufs* p) {
   const int64_t M = R * S;
   p->R = R; p->M = M; p->S = S;
   p->X4 = b.take_bytes(M * X4W * es);
-  for (int i = 1; i <= 8; ++i) p->Hs[i] = (i == 4) ? p->X4 : b.take_bytes(M * W * es);
+  // forward-only in bf16 mode: the fused trunk keeps H1..H8 on chip, only the PE columns of X4 exist
+  const bool on_chip = !keep && es == 2;
+  for (int i = 1; i <= 8; ++i) p->Hs[i] = (i == 4) ? p->X4 : (on_chip ? nullptr : b.take_bytes(M * W * es));
   p->Hs[0] = nullptr;
   p->HF = b.take_bytes(M * W * es);
   p->G1 = b.take_bytes(M * H * es);
@@ -139,7 +141,7 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, PassBu
   p->csig = b.take<float>(M);
   p->rgb = b.take<float>(M * 3);
   p->z = b.take<float>(M);
-  p->relu_mask = b.take<uint32_t>(es == 2 ? upnerf_trunk_mask_words(M) : 0);
+  p->relu_mask = (es == 2 && keep) ? b.take<uint32_t>(upnerf_trunk_mask_words(M)) : nullptr;
   p->HFr = b.take<float>(R * W);
   p->G2r = b.take<float>(R * H);
   p->Wsum = b.take<float>(R);
@@ -245,9 +247,10 @@ int make_plan(const upnerf_render_args& a, void* base, Plan* pl) {
   UPNERF_REQUIRE((a.n_rays * a.n_samples) % 8 == 0, UPNERF_ERR_BAD_SHAPE,
                  "n_rays*n_samples must be a multiple of 8");
   Bump b{static_cast<uint8_t*>(base), 0};
-  carve_pass(b, a.n_rays, a.n_samples, pl->es, pl->L, &pl->coarse);
-  if (a.n_importance > 0) carve_pass(b, a.n_rays, pl->S_f, pl->es, pl->L, &pl->fine);
-  carve_scratch(b, a.n_rays, a.n_importance > 0 ? pl->S_f : a.n_samples, pl->es, pl->L, &pl->scratch);
+  const bool keep = !a.no_grad;
+  carve_pass(b, a.n_rays, a.n_samples, pl->es, pl->L, keep, &pl->coarse);
+  if (a.n_importance > 0) carve_pass(b, a.n_rays, pl->S_f, pl->es, pl->L, keep, &pl->fine);
+  if (keep) carve_scratch(b, a.n_rays, a.n_importance > 0 ? pl->S_f : a.n_samples, pl->es, pl->L, &pl->scratch);
   pl->bytes = b.off + 256;
   return UPNERF_OK;
 }
@@ -418,7 +421,7 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     ta.wcat = k.Wcat; ta.ld_w = WCAT;
     for (int i = 0; i < 8; ++i) {
       ta.bias[i] = prm + L.bl[i];
-      ta.out[i] = p.Hs[i + 1];
+      ta.out[i] = a.no_grad ? nullptr : p.Hs[i + 1];
       ta.ld_out[i] = (i + 1 == 4) ? X4W : W;
     }
     ta.bias[8] = prm + L.bf;
@@ -786,6 +789,7 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
   UPNERF_TRY(check_common(*a));
   Plan pl;
   UPNERF_TRY(make_plan(*a, a->workspace, &pl));
+  UPNERF_REQUIRE(!a->no_grad, UPNERF_ERR_BAD_CONFIG, "render_bwd: the forward ran with no_grad (nothing was kept)");
   UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE, "workspace too small");
   Ctx c{a->dtype, pl.es, as_stream(stream)};
   const Phase ph = make_phase(a->cfg, a->sched_mult);

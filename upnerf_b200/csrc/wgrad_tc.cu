@@ -257,7 +257,7 @@ extern "C" int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, in
     attr_set = true;
   }
   dim3 grid(chunks, splits);
-  LaunchScope scope(kCatWgradTc, as_stream(stream), 2.0 * M * N * K);
+  LaunchScope scope(kCatWgradTc, as_stream(stream), 2.0 * M * N * K, 2.0 * M * (N + K) + 4.0 * N * K);
   wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmY, tmX, args);
   UPNERF_CHECK_LAUNCH("wgrad_tc_kernel");
   return UPNERF_OK;

@@ -88,6 +88,7 @@ class _RenderFn(torch.autograd.Function):
         a.sched_mult = float(meta["sched_mult"])
         a.use_disp = int(meta["use_disp"])
         a.perturb = float(meta["perturb"])
+        a.no_grad = int(meta["no_grad"])
         keep = [rays, meta["img_idx"], flat_c, flat_f, emb_ca, emb_fa, emb_cc, emb_fc,
                 meta["perturb_rand"], meta["u0"], meta["u1"]]
         a.rays, a.img_idx = L._vp(rays), L._vp(meta["img_idx"])
@@ -186,7 +187,7 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
                 sched_mult=m, use_disp=use_disp, perturb=perturb, keys=_phase_keys(cfg, m),
                 img_idx=img_idx.contiguous().long(), perturb_rand=as_f32(perturb_rand), u0=as_f32(u0),
                 u1=as_f32(u1), dtype=_dtype_code(kwargs.get("precision") or default_precision()),
-                n_images=0)
+                n_images=0, no_grad=False)
     emb = lambda k: embeddings[k].weight if k in embeddings else None
     ea_c = emb("coarse_a") if coarse.encode_appearance else None
     ec_c = emb("coarse_c") if coarse.encode_candidate else None
@@ -197,6 +198,9 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
             meta["n_images"] = e.shape[0]
     flat_c = flat_parameters(coarse)
     flat_f = flat_parameters(fine) if fine is not None else None
+    # inference (the reference's validation / tto render runs under no_grad): nothing is kept for backward
+    meta["no_grad"] = not (torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (rays, flat_c, flat_f, ea_c, ea_f, ec_c, ec_f)))
     outs = _RenderFn.apply(meta, rays.contiguous().float(), flat_c, flat_f, ea_c, ea_f, ec_c, ec_f)
     results, it = {}, iter(outs)
     for which in ("coarse", "fine") if fine is not None else ("coarse",):
