@@ -179,15 +179,27 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       mbar_wait(bar_done, 0);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-      float* wrow = args.dW + static_cast<int64_t>(n) * args.lddw;
+      // Transpose the 128 x K fp32 tile through shared memory (the operand stages are idle now:
+      // every TMA load has landed and every MMA has retired) so that the reduction into dW is
+      // COALESCED: one warp per output row, lanes on consecutive columns.  Thread-per-row
+      // atomics straight from TMEM would be 32 scattered 4-byte transactions per instruction.
+      float* sT = reinterpret_cast<float*>(sStage);
+      const int ldt = K + 1;  // +1: the row-strided writes below hit 32 different banks
       for (int g = 0; g < K / 32; ++g) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + g * 32, v);
         tmem_ld_wait();
+        float* dst = sT + (quad * 32 + lane) * ldt + g * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int d = sMap[g * 32 + i];
-          if (d >= 0) atomicAdd(wrow + d, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) dst[i] = __uint_as_float(v[i]);
+      }
+      named_bar_sync(1, 128);
+      for (int r = warp - 2; r < 128; r += 4) {
+        const float* src = sT + r * ldt;
+        float* wrow = args.dW + static_cast<int64_t>(chunk * 128 + r) * args.lddw;
+        for (int c = lane; c < K; c += 32) {
+          const int d = sMap[c];
+          if (d >= 0) atomicAdd(wrow + d, src[c]);
         }
       }
       if (args.db) {
