@@ -284,20 +284,20 @@ def main():
     # ---- per-kernel-family device time (CUDA events on the launching stream) ------------------
     import ctypes as C
 
+    # (every rank runs these steps: training_step contains the gradient all-reduce, a collective)
     prof = {}
-    if rank == 0:
-        lib.upnerf_profile_enable(1)
-        n_prof = min(K, 5)
-        for i in range(n_prof):
-            system.training_step(dev_batches[i % n_batches], i)
-        torch.cuda.synchronize()
-        n = len(CATS)
-        ms_a, ln_a, wk_a, by_a = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)(), (C.c_double * n)()
-        L.check(lib.upnerf_profile_collect(ms_a, ln_a, wk_a, by_a, n), "upnerf_profile_collect")
-        lib.upnerf_profile_enable(0)
-        for i, c in enumerate(CATS):
-            prof[c] = {"ms_per_step": ms_a[i] / n_prof, "launches_per_step": ln_a[i] / n_prof,
-                       "work_per_step": wk_a[i] / n_prof, "bytes_per_step": by_a[i] / n_prof}
+    lib.upnerf_profile_enable(1)
+    n_prof = min(K, 5)
+    for i in range(n_prof):
+        system.training_step(dev_batches[i % n_batches], i)
+    torch.cuda.synchronize()
+    n = len(CATS)
+    ms_a, ln_a, wk_a, by_a = (C.c_double * n)(), (C.c_longlong * n)(), (C.c_double * n)(), (C.c_double * n)()
+    L.check(lib.upnerf_profile_collect(ms_a, ln_a, wk_a, by_a, n), "upnerf_profile_collect")
+    lib.upnerf_profile_enable(0)
+    for i, c in enumerate(CATS):
+        prof[c] = {"ms_per_step": ms_a[i] / n_prof, "launches_per_step": ln_a[i] / n_prof,
+                   "work_per_step": wk_a[i] / n_prof, "bytes_per_step": by_a[i] / n_prof}
     if world > 1:
         dist.barrier()
 

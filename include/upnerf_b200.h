@@ -151,6 +151,14 @@ int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, 
                       const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
                       void* stream);
 
+/* Same for two layers stacked along N (N = 256): output rows 0..127 accumulate into dW_lo
+ * (row stride lddw_lo), rows 128..255 into dW_hi -- the candidate / rgb head layers share
+ * their input (models/nerf.py:97,106), so one pass over it serves both weight gradients. */
+int upnerf_wgrad2_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW_lo,
+                       int64_t lddw_lo, float* dW_hi, int64_t lddw_hi, int64_t M, int K, int n_seg,
+                       const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
+                       void* stream);
+
 /* fp32 SIMT GEMM with arbitrary element strides (validation mode and the small per-ray
  * products):  C[m*scm + n*scn] = epi( sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] ).
  * split_k > 1 splits the k range over grid.z and accumulates with atomicAdd into C

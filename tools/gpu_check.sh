@@ -5,5 +5,5 @@ timeout -s KILL 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_last.json').read())
-print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['families_ms_per_step'])
+print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'], d['roofline_mlp']['fused_trunk']['frac'], d['roofline_mlp']['families_ms_per_step'])
 PY

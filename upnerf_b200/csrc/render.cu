@@ -95,11 +95,16 @@ constexpr int WCATT = UPNERF_TRUNK_WCATT_COLS;  // transposed trunk weights in b
 struct Packed {  // GEMM operands derived from the fp32 parameters (element type T)
   void* Wcat;                                           // [256, WCAT]: W1|W2|W3|W4|W5=[h|PE]|W6|W7|W8|WF
   void *W1, *Wk[8], *W5, *WF;                           // views into Wcat (row stride WCAT)
-  void *Wc1, *Wc2, *Wq;                                 // [N, K] K-major
+  void* Wcq;                                            // [256, 256]: [Wc1; Wq] stacked along N (views below)
+  void *Wc1, *Wq;                                       // [128, 256] K-major, rows 0..127 / 128..255 of Wcq
+  void* Wc2;                                            // [128, 128]
   void* WcatT;                                          // [256, WCATT]: WF^T|W8^T|W7^T|W6^T|W5h^T|W4^T|W3^T|W2^T
   void *WkT[8], *W5T, *WFT;                             // views into WcatT (row stride WCATT); W5T = h part
   void *W1T, *W5peT;                                    // [64, 256]: rows = PE columns (for dPE)
-  void *Wc1T, *Wc2T, *WqT;                              // transposed for the data gradient
+  void* WcqT;                                           // [256, 256]: [Wc1^T | Wq^T] side by side along K
+  void *Wc1T, *WqT;                                     // [256, 128] views (row stride 256)
+  void* Wc2T;
+  float* hw3;                                           // [3, 256] fp32: rgb_share_layer.2 weights on columns 128..255
   float* Wq32;      // [128,256] fp32 folded rgb weight
   float* bq_const;  // [128]
   float* band_xyz;  // [16]
@@ -134,9 +139,11 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool k
   for (int i = 1; i <= 8; ++i) p->Hs[i] = (i == 4) ? p->X4 : (on_chip ? nullptr : b.take_bytes(M * W * es));
   p->Hs[0] = nullptr;
   p->HF = b.take_bytes(M * W * es);
-  p->G1 = b.take_bytes(M * H * es);
+  // candidate and rgb hidden layers side by side in one [M, 256] buffer: G1 = columns 0..127,
+  // Q = columns 128..255 (both with row stride 256), so the two layers can run as one stacked GEMM
+  p->G1 = b.take_bytes(M * 2 * H * es);
+  p->Q = p->G1 ? static_cast<uint8_t*>(p->G1) + H * es : nullptr;
   p->G2 = b.take_bytes(M * H * es);
-  p->Q = b.take_bytes(M * H * es);
   p->ssig = b.take<float>(M);
   p->csig = b.take<float>(M);
   p->rgb = b.take<float>(M * 3);
@@ -148,8 +155,9 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool k
   p->Wcsum = b.take<float>(R);
   p->P = b.take<float>(R * (L.in_dir + L.ad));
   p->Crows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
-  p->Bq = b.take<float>(R * H);
-  p->Bc = b.take<float>(R * H);
+  // per-ray biases: stacked mode [R, 256] rows [Bc | Bq]; otherwise two contiguous [R, 128] blocks
+  p->Bc = b.take<float>(R * 2 * H);
+  p->Bq = p->Bc ? p->Bc + R * H : nullptr;
   Packed& k = p->pk;
   k.Wq32 = b.take<float>(H * W);
   k.bq_const = b.take<float>(H);
@@ -192,12 +200,15 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool k
   }
   k.W1T = b.take_bytes(PEW * W * es);
   k.W5peT = b.take_bytes(PEW * W * es);
-  k.Wc1 = b.take_bytes(H * W * es);
-  k.Wc1T = b.take_bytes(W * H * es);
+  k.Wcq = b.take_bytes(2 * H * W * es);
+  k.Wc1 = k.Wcq;
+  k.Wq = k.Wcq ? static_cast<uint8_t*>(k.Wcq) + static_cast<uint64_t>(H) * W * es : nullptr;
+  k.WcqT = b.take_bytes(W * 2 * H * es);
+  k.Wc1T = k.WcqT;
+  k.WqT = k.WcqT ? static_cast<uint8_t*>(k.WcqT) + H * es : nullptr;
   k.Wc2 = b.take_bytes(H * H * es);
   k.Wc2T = b.take_bytes(H * H * es);
-  k.Wq = b.take_bytes(H * W * es);
-  k.WqT = b.take_bytes(W * H * es);
+  k.hw3 = b.take<float>(3 * 2 * H);
   k.region_bytes = b.off - start;
 }
 
@@ -208,8 +219,8 @@ void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scr
   for (int j = 0; j < 8; ++j) s->dY[j] = (es == 2 || j < 2) ? b.take_bytes(M * W * es) : nullptr;
   s->dHF = b.take_bytes(M * W * es);
   s->dG2p = b.take_bytes(M * H * es);
-  s->dG1p = b.take_bytes(M * H * es);
-  s->dQp = b.take_bytes(M * H * es);
+  s->dG1p = b.take_bytes(M * 2 * H * es);   // [dG1p | dQp], row stride 256
+  s->dQp = s->dG1p ? static_cast<uint8_t*>(s->dG1p) + H * es : nullptr;
   s->dPE = b.take_bytes(M * PEW * es);
   s->dssig = b.take<float>(M);
   s->dcsig = b.take<float>(M);
@@ -374,7 +385,7 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
   add(prm + L.Wf, W, k.WFT, WCATT, W, W, 1);
   if (ph.cand) {
     add(prm + L.Wc0, W + L.cd, k.Wc1, W, H, W, 0);
-    add(prm + L.Wc0, W + L.cd, k.Wc1T, H, H, W, 1);
+    add(prm + L.Wc0, W + L.cd, k.Wc1T, 2 * H, H, W, 1);
     add(prm + L.Wc2, H, k.Wc2, H, H, H, 0);
     add(prm + L.Wc2, H, k.Wc2T, H, H, H, 1);
   }
@@ -386,12 +397,12 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
       e.bias = prm + L.br0;
       UPNERF_TRY(mm(c, prm + L.bsf, 0, 1, prm + L.Wr0, L.rgb_in, 1, k.bq_const, 0, 1, 1, H, L.F, &e, 0));
       add(k.Wq32, W, k.Wq, W, H, W, 0);
-      add(k.Wq32, W, k.WqT, H, H, W, 1);
+      add(k.Wq32, W, k.WqT, 2 * H, H, W, 1);
     } else {
       UPNERF_CHECK_CUDA(cudaMemcpyAsync(k.bq_const, prm + L.br0, H * sizeof(float),
                                         cudaMemcpyDeviceToDevice, c.st));
       add(prm + L.Wr0, L.rgb_in, k.Wq, W, H, W, 0);
-      add(prm + L.Wr0, L.rgb_in, k.WqT, H, H, W, 1);
+      add(prm + L.Wr0, L.rgb_in, k.WqT, 2 * H, H, W, 1);
     }
   }
   return run_pack(pl, c.dtype, c.st);
@@ -459,26 +470,20 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     UPNERF_TRY(linear(c, p.Hs[8], W, k.WF, WCAT, p.HF, W, M, W, W, e));
   }
 
+  // Head layers on HF.  candidate_encoding.0 and (folded) rgb_share_layer.0 read the same input, so
+  // with both live (phase 1) they run as ONE stacked 256-wide GEMM into the side-by-side buffer
+  // [G1 | Q]; per-ray inputs (embeddings, direction encoding) enter as a per-ray bias.
+  const int H2 = 2 * H;
+  const bool stack = ph.cand && ph.rgb && c.dtype == UPNERF_BF16;
+  float* Bc = p.Bc;
+  float* Bq = stack ? p.Bc + H : p.Bq;
+  const int64_t ldbias = stack ? H2 : H;
   if (ph.cand) {
     // per-ray bias of candidate_encoding.0: W[:, 256:] c_emb + b
     UPNERF_TRY(gather_rows(io.emb_c, a.img_idx, R, L.cd, p.Crows, L.cd, c.st));
     e = ep_none();
     e.bias = prm + L.bc0;
-    UPNERF_TRY(mm(c, p.Crows, L.cd, 1, prm + L.Wc0 + W, W + L.cd, 1, p.Bc, H, 1, R, H, L.cd, &e, 0));
-    e = ep_none();
-    e.act = 1;
-    e.ray_bias = p.Bc;
-    e.rows_per_ray = S;
-    UPNERF_TRY(linear(c, p.HF, W, k.Wc1, W, p.G1, H, M, H, W, e));
-    e = ep_none();
-    e.act = 1;
-    e.bias = prm + L.bc2;
-    e.n_heads = 1;
-    e.head_w = prm + L.Wcs;
-    e.head_b = prm + L.bcs;
-    e.head_act = 1;
-    e.head_out = p.csig;
-    UPNERF_TRY(linear(c, p.G1, H, k.Wc2, H, p.G2, H, M, H, H, e));
+    UPNERF_TRY(mm(c, p.Crows, L.cd, 1, prm + L.Wc0 + W, W + L.cd, 1, Bc, ldbias, 1, R, H, L.cd, &e, 0));
   }
   if (ph.rgb) {
     // per-ray bias of rgb_share_layer.0: W[:, F:] [PE(dir) | a_emb] + (W[:, :F] b_sf + b)
@@ -491,17 +496,54 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     const int front = cfg.encode_feat ? L.F : W;
     e = ep_none();
     e.bias = k.bq_const;
-    UPNERF_TRY(mm(c, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, p.Bq, H, 1, R, H, pw, &e, 0));
+    UPNERF_TRY(mm(c, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, Bq, ldbias, 1, R, H, pw, &e, 0));
+  }
+  if (stack) {
+    // rgb_share_layer.2 row-dots see only the Q half of the stacked output
+    UPNERF_CHECK_CUDA(cudaMemsetAsync(k.hw3, 0, 3 * H2 * sizeof(float), c.st));
+    UPNERF_CHECK_CUDA(cudaMemcpy2DAsync(k.hw3 + H, H2 * sizeof(float), prm + L.Wr2, H * sizeof(float),
+                                        H * sizeof(float), 3, cudaMemcpyDeviceToDevice, c.st));
     e = ep_none();
     e.act = 1;
-    e.ray_bias = p.Bq;
+    e.ray_bias = Bc;
     e.rows_per_ray = S;
     e.n_heads = 3;
-    e.head_w = prm + L.Wr2;
+    e.head_w = k.hw3;
     e.head_b = prm + L.br2;
     e.head_act = 2;
     e.head_out = p.rgb;
-    UPNERF_TRY(linear(c, p.HF, W, k.Wq, W, p.Q, H, M, H, W, e));
+    UPNERF_TRY(linear(c, p.HF, W, k.Wcq, W, p.G1, H2, M, H2, W, e));
+  } else {
+    if (ph.cand) {
+      e = ep_none();
+      e.act = 1;
+      e.ray_bias = Bc;
+      e.rows_per_ray = S;
+      UPNERF_TRY(linear(c, p.HF, W, k.Wc1, W, p.G1, H2, M, H, W, e));
+    }
+    if (ph.rgb) {
+      e = ep_none();
+      e.act = 1;
+      e.ray_bias = Bq;
+      e.rows_per_ray = S;
+      e.n_heads = 3;
+      e.head_w = prm + L.Wr2;
+      e.head_b = prm + L.br2;
+      e.head_act = 2;
+      e.head_out = p.rgb;
+      UPNERF_TRY(linear(c, p.HF, W, k.Wq, W, p.Q, H2, M, H, W, e));
+    }
+  }
+  if (ph.cand) {
+    e = ep_none();
+    e.act = 1;
+    e.bias = prm + L.bc2;
+    e.n_heads = 1;
+    e.head_w = prm + L.Wcs;
+    e.head_b = prm + L.bcs;
+    e.head_act = 1;
+    e.head_out = p.csig;
+    UPNERF_TRY(linear(c, p.G1, H2, k.Wc2, H, p.G2, H, M, H, H, e));
   }
 
   // compositing
@@ -581,17 +623,15 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   bool dhf_live = feat_grad;          // does dHF hold a gradient yet?
   bool dg2_from_feat = feat_grad && ph.cand;
 
-  // 3. rgb head
+  const int H2 = 2 * H;
+  const bool stack = ph.cand && ph.rgb && c.dtype == UPNERF_BF16;
+  const int pw = L.in_dir + L.ad;
+  const int front = cfg.encode_feat ? L.F : W;
+
+  // 3. rgb head, part 1: through the sigmoid / row-dots / ReLU -> dQ_pre (right half of [dG1p | dQp])
   if (ph.rgb) {
-    UPNERF_TRY(rgb_head_bwd(p.Q, H, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H, s.dBq, g + L.Wr2,
+    UPNERF_TRY(rgb_head_bwd(p.Q, H2, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H2, s.dBq, g + L.Wr2,
                             g + L.br2, c.dtype, c.st));
-    // dHF (+)= dQp Wq
-    e = ep_none();
-    if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
-    UPNERF_TRY(linear(c, s.dQp, H, k.WqT, H, s.dHF, W, M, W, H, e));
-    dhf_live = true;
-    const int pw = L.in_dir + L.ad;
-    const int front = cfg.encode_feat ? L.F : W;
     // per-ray bias path: [PE(dir) | a_emb] columns of rgb_share_layer.0 and the appearance table
     UPNERF_TRY(mm(c, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
     if (L.ad > 0 && io.d_emb_a) {
@@ -601,45 +641,64 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dbq, 0, H * sizeof(float), c.st));
     UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, s.dbq, nullptr, UPNERF_F32, c.st));
     UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, c.st));
-    if (cfg.encode_feat) {
-      // weight gradient of the folded matrix, then the chain rule into W_rgb0[:, :F] and W_sf
-      UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
-      const Seg sg{0, W, 0};
-      UPNERF_TRY(wgrad(c, s.dQp, H, p.HF, W, s.dWq, W, nullptr, M, H, W, &sg, 1));
-      UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
-      UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
-      // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
-      UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
-      UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
-    } else {
-      const Seg sg{0, W, 0};
-      UPNERF_TRY(wgrad(c, s.dQp, H, p.HF, W, g + L.Wr0, L.rgb_in, nullptr, M, H, W, &sg, 1));
-    }
+    if (cfg.encode_feat) UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
   }
 
-  // 4. candidate head
+  // 4. candidate head, part 1: candidate_sigma and candidate_encoding.2 -> dG1_pre (left half)
   if (ph.cand) {
     UPNERF_REQUIRE(dg2_from_feat, UPNERF_ERR_BAD_CONFIG, "candidate head without the feature path");
     // candidate_sigma: dw += sum dcsig g2, db += sum dcsig
     UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, c.st));
     const Seg sgH{0, H, 0};
-    UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
+    UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H2, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
     e = ep_none();
-    e.aux = p.G1; e.ldaux = H; e.aux_mode = 2;
-    UPNERF_TRY(linear(c, s.dG2p, H, k.Wc2T, H, s.dG1p, H, M, H, H, e));
-    const Seg sgW{0, W, 0};
-    UPNERF_TRY(wgrad(c, s.dG1p, H, p.HF, W, g + L.Wc0, W + L.cd, nullptr, M, H, W, &sgW, 1));
-    UPNERF_TRY(ray_sum128(s.dG1p, H, R, S, s.dBc, c.dtype, c.st));
+    e.aux = p.G1; e.ldaux = H2; e.aux_mode = 2;
+    UPNERF_TRY(linear(c, s.dG2p, H, k.Wc2T, H, s.dG1p, H2, M, H, H, e));
+    UPNERF_TRY(ray_sum128(s.dG1p, H2, R, S, s.dBc, c.dtype, c.st));
     UPNERF_TRY(mm(c, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
     UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, c.st));
     if (io.d_emb_c) {
       UPNERF_TRY(mm(c, s.dBc, H, 1, prm + L.Wc0 + W, 1, W + L.cd, s.dCrows, L.cd, 1, R, L.cd, H, nullptr, 0));
       UPNERF_TRY(scatter_add_rows(s.dCrows, L.cd, a.img_idx, R, L.cd, io.d_emb_c, c.st));
     }
+  }
+
+  // 4b. the two head layers on HF: weight gradients and dHF (+)= [dG1p | dQp] [Wc1; Wq]
+  float* dWq_dst = cfg.encode_feat ? s.dWq : g + L.Wr0;
+  const int64_t ld_dWq = cfg.encode_feat ? W : L.rgb_in;
+  const Seg sgW{0, W, 0};
+  if (stack) {
+    int src = 0, len = W, dst = 0;
+    UPNERF_TRY(upnerf_wgrad2_bf16(s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, dWq_dst, ld_dWq, M, W, 1, &src, &len,
+                                  &dst, c.st));
     e = ep_none();
     if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
-    UPNERF_TRY(linear(c, s.dG1p, H, k.Wc1T, H, s.dHF, W, M, W, H, e));
+    UPNERF_TRY(linear(c, s.dG1p, H2, k.WcqT, H2, s.dHF, W, M, W, H2, e));
     dhf_live = true;
+  } else {
+    if (ph.rgb) {
+      UPNERF_TRY(wgrad(c, s.dQp, H2, p.HF, W, dWq_dst, ld_dWq, nullptr, M, H, W, &sgW, 1));
+      e = ep_none();
+      if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
+      UPNERF_TRY(linear(c, s.dQp, H2, k.WqT, H2, s.dHF, W, M, W, H, e));
+      dhf_live = true;
+    }
+    if (ph.cand) {
+      UPNERF_TRY(wgrad(c, s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, nullptr, M, H, W, &sgW, 1));
+      e = ep_none();
+      if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
+      UPNERF_TRY(linear(c, s.dG1p, H2, k.Wc1T, H2, s.dHF, W, M, W, H, e));
+      dhf_live = true;
+    }
+  }
+
+  // 4c. rgb head, part 2: chain rule through the folded matrix Wq = W_rgb0[:, :F] W_sf
+  if (ph.rgb && cfg.encode_feat) {
+    UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
+    UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
+    // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
+    UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
+    UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
   }
 
   // 5. xyz_encoding_final + share_sigma  ->  dH8_pre

@@ -46,6 +46,8 @@ constexpr int kMaxSeg = 4;
 struct WgradArgs {
   float* dW;
   int64_t lddw;
+  float* dW_hi;      // optional: destination of output rows 128..255 (two stacked layers)
+  int64_t lddw_hi;
   float* db;
   int64_t M;
   int N;
@@ -196,7 +198,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       named_bar_sync(1, 128);
       for (int r = warp - 2; r < 128; r += 4) {
         const float* src = sT + r * ldt;
-        float* wrow = args.dW + static_cast<int64_t>(chunk * 128 + r) * args.lddw;
+        float* wrow = (chunk == 1 && args.dW_hi) ? args.dW_hi + static_cast<int64_t>(r) * args.lddw_hi
+                                                  : args.dW + static_cast<int64_t>(chunk * 128 + r) * args.lddw;
         for (int c = lane; c < K; c += 32) {
           const int d = sMap[c];
           if (d >= 0) atomicAdd(wrow + d, src[c]);
@@ -222,10 +225,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 }  // namespace
 }  // namespace upnerf
 
+namespace upnerf {
+int wgrad_launch(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                 float* dW_hi, int64_t lddw_hi, float* db, int64_t M, int N, int K, int n_seg,
+                 const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host, void* stream);
+}
 extern "C" int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx,
                                  float* dW, int64_t lddw, float* db, int64_t M, int N, int K,
                                  int n_seg, const int* seg_src_host, const int* seg_len_host,
                                  const int* seg_dst_host, void* stream) {
+  return upnerf::wgrad_launch(dY, lddy, X, ldx, dW, lddw, nullptr, 0, db, M, N, K, n_seg, seg_src_host,
+                              seg_len_host, seg_dst_host, stream);
+}
+extern "C" int upnerf_wgrad2_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx,
+                                  float* dW_lo, int64_t lddw_lo, float* dW_hi, int64_t lddw_hi,
+                                  int64_t M, int K, int n_seg, const int* seg_src_host,
+                                  const int* seg_len_host, const int* seg_dst_host, void* stream) {
+  UPNERF_REQUIRE(dW_lo && dW_hi, UPNERF_ERR_BAD_SHAPE, "wgrad2_bf16: both destinations are required");
+  return upnerf::wgrad_launch(dY, lddy, X, ldx, dW_lo, lddw_lo, dW_hi, lddw_hi, nullptr, M, 256, K, n_seg,
+                              seg_src_host, seg_len_host, seg_dst_host, stream);
+}
+int upnerf::wgrad_launch(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                         float* dW_hi, int64_t lddw_hi, float* db, int64_t M, int N, int K, int n_seg,
+                         const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
+                         void* stream) {
   using namespace upnerf;
   UPNERF_REQUIRE(M > 0, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: M=%lld", (long long)M);
   UPNERF_REQUIRE(N >= 128 && N <= 256 && N % 128 == 0, UPNERF_ERR_BAD_SHAPE,
@@ -238,6 +261,8 @@ extern "C" int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, in
   memset(&args, 0, sizeof(args));
   args.dW = dW;
   args.lddw = lddw;
+  args.dW_hi = dW_hi;
+  args.lddw_hi = lddw_hi;
   args.db = db;
   args.M = M;
   args.N = N;
