@@ -17,6 +17,27 @@ __device__ __forceinline__ float ldv(const __nv_bfloat16* p) { return __bfloat16
 __device__ __forceinline__ void stv(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stv(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// four consecutive elements (16-byte / 8-byte aligned) as one memory transaction
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 t;
+  *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(v[0], v[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
 __device__ __forceinline__ float softplus_ref(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -77,6 +98,7 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
   float ab[3] = {0.f, 0.f, 0.f};
   for (int64_t r = blockIdx.x * 8ll + warp; r < R; r += gridDim.x * 8ll) {
     float rb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int s = 0; s < S; ++s) {
       const int64_t m = r * S + s;
       float g[3];
@@ -86,18 +108,17 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
         g[h] = d_rgb[m * 3 + h] * y * (1.f - y);
         ab[h] += g[h];
       }
-      const T* q = Q + m * ldq + lane * 4;
-      T* dq = dQ + m * lddq + lane * 4;
+      float qv[4], d[4];
+      ld4(Q + m * ldq + lane * 4, qv);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float qv = ldv(q + e);
-        const float d = qv > 0.f ? (g[0] * w2[0][e] + g[1] * w2[1][e] + g[2] * w2[2][e]) : 0.f;
-        stv(dq + e, d);
-        rb[e] += d;
-        aw[0][e] += g[0] * qv;
-        aw[1][e] += g[1] * qv;
-        aw[2][e] += g[2] * qv;
+        d[e] = qv[e] > 0.f ? (g[0] * w2[0][e] + g[1] * w2[1][e] + g[2] * w2[2][e]) : 0.f;
+        rb[e] += d[e];
+        aw[0][e] += g[0] * qv[e];
+        aw[1][e] += g[1] * qv[e];
+        aw[2][e] += g[2] * qv[e];
       }
+      st4(dQ + m * lddq + lane * 4, d);
     }
     float* o = d_raybias + r * 128 + lane * 4;
 #pragma unroll
