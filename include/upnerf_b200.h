@@ -151,6 +151,16 @@ int upnerf_wgrad_bf16(const void* dY, int64_t lddy, const void* X, int64_t ldx, 
                       const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
                       void* stream);
 
+/* Deterministic variant: every CTA parks its split partial in `workspace`
+ * (>= upnerf_wgrad_det_workspace_bytes(N, K)) and a second launch sums the splits in a fixed order
+ * -- bit-reproducible, no atomics.  upnerf_render_bwd uses this mode for every weight gradient,
+ * with ONE reduction launch per network pass. */
+uint64_t upnerf_wgrad_det_workspace_bytes(int N, int K);
+int upnerf_wgrad_bf16_det(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
+                          int64_t lddw, float* db, int64_t M, int N, int K, int n_seg,
+                          const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
+                          void* workspace, uint64_t workspace_bytes, void* stream);
+
 /* Same for two layers stacked along N (N = 256): output rows 0..127 accumulate into dW_lo
  * (row stride lddw_lo), rows 128..255 into dW_hi -- the candidate / rgb head layers share
  * their input (models/nerf.py:97,106), so one pass over it serves both weight gradients. */

@@ -111,6 +111,36 @@ def test_wgrad_bf16(cuda_dev, M, N, K):
     assert torch.allclose(db / scale, dY.float().sum(0) / scale, rtol=1e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (64 * 1001, 256, 320), (8192, 128, 256),
+                                   (12288, 256, 64), (64 * 77, 128, 128), (64 * 3, 256, 256)])
+def test_wgrad_bf16_deterministic(cuda_dev, M, N, K):
+    """Atomic-free split reduction (the mode upnerf_render_bwd uses): same result as the atomic
+    kernel within fp32 summation-order noise, accumulates into dW (+=), and is bit-reproducible."""
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M + K + 1)
+    dY = _bf16(torch.randn(M, N, generator=g)).to(cuda_dev)
+    X = _bf16(torch.randn(M, K, generator=g)).to(cuda_dev)
+    if K > 64:
+        segs, kw = [(0, K - 64, 63), (K - 64, 63, 0)], K - 1
+    else:
+        segs, kw = [(0, 63, 0)], 63
+    init = torch.randn(N, kw, generator=g).to(cuda_dev)
+    outs = []
+    for _ in range(2):
+        dW = init.clone()
+        db = torch.ones(N, device=cuda_dev)
+        L.wgrad_bf16_det(dY, X, dW, db, M, N, K, segs)
+        torch.cuda.synchronize()
+        outs.append((dW, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    full = dY.float().t() @ X.float()
+    ref = torch.cat([full[:, K - 64:K - 1], full[:, :K - 64]], 1) if K > 64 else full[:, :63]
+    scale = M ** 0.5
+    assert torch.allclose((outs[0][0] - init) / scale, ref / scale, rtol=1e-3, atol=2e-3)
+    assert torch.allclose((outs[0][1] - 1) / scale, dY.float().sum(0) / scale, rtol=1e-3, atol=2e-3)
+
+
 @pytest.mark.parametrize("trans", ["nt", "nn", "tn"])
 def test_gemm_f32_strided(cuda_dev, trans):
     from upnerf_b200 import _lib as L

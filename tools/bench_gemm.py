@@ -24,6 +24,9 @@ def timeit(fn, iters=10, warm=3):
 def main():
     dev = torch.device("cuda:0")
     M = 4096 * 192
+    for a in sys.argv[1:]:
+        if a.startswith("M="):
+            M = int(a[2:])
     only_trunk = "trunk" in sys.argv[1:]
     for (N, K, aux) in [] if only_trunk else [(256, 256, 0), (256, 256, 2), (256, 64, 0), (256, 320, 0), (128, 256, 0), (64, 256, 0)]:
         A = torch.randn(M, K, device=dev).bfloat16()
@@ -47,8 +50,12 @@ def main():
         fl = 2.0 * M * N * K
         by = (M * K + M * N) * 2
         print(f"wgrad_bf16 M={M} N={N} K={K}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.0f} GB/s")
+        ms = timeit(lambda: L.wgrad_bf16_det(dY, X, dW, db, M, N, K, [(0, K, 0)]))
+        print(f"wgrad_bf16_det (partials + reduce launch) M={M} N={N} K={K}: {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s")
         ms = timeit(lambda: torch.matmul(dY.t(), X))
         print(f"   torch.matmul bf16: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    if "wgrad" in sys.argv[1:]:
+        return
     # fused trunk forward
     pe = torch.randn(M, 64, device=dev).bfloat16()
     ks = [64, 256, 256, 256, 320, 256, 256, 256, 256]

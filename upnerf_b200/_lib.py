@@ -125,6 +125,28 @@ def wgrad_bf16(dY, X, dW, db, M, N, K, segs, lddy=None, ldx=None, lddw=None):
     check(st, "upnerf_wgrad_bf16")
 
 
+def wgrad_bf16_det(dY, X, dW, db, M, N, K, segs, lddy=None, ldx=None, lddw=None):
+    """Deterministic (atomic-free) variant of `wgrad_bf16` (see upnerf_wgrad_bf16_det)."""
+    import torch
+
+    lddy = dY.stride(0) if lddy is None else lddy
+    ldx = X.stride(0) if ldx is None else ldx
+    lddw = dW.stride(0) if lddw is None else lddw
+    n = len(segs)
+    arr = C.c_int * n
+    src = arr(*[s[0] for s in segs])
+    ln = arr(*[s[1] for s in segs])
+    dst = arr(*[s[2] for s in segs])
+    f = lib().upnerf_wgrad_det_workspace_bytes
+    f.restype = C.c_uint64
+    nbytes = int(f(C.c_int(N), C.c_int(K)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dY.device)
+    st = lib().upnerf_wgrad_bf16_det(ptr(dY), _i64(lddy), ptr(X), _i64(ldx), ptr(dW), _i64(lddw),
+                                     ptr(db), _i64(M), C.c_int(N), C.c_int(K), C.c_int(n), src, ln, dst,
+                                     ptr(ws), C.c_uint64(nbytes), stream_ptr())
+    check(st, "upnerf_wgrad_bf16_det")
+
+
 def gemm_f32(A, sa, B, sb, C_out, sc, M, N, K, ep: Epilogue | None = None, accumulate=False,
              split_k=1):
     """Strided fp32 SIMT GEMM (see upnerf_gemm_f32). sa=(sam,sak), sb=(sbn,sbk), sc=(scm,scn)."""

@@ -19,6 +19,39 @@ struct PackList {
 };
 
 int run_pack(const PackList& list, int dtype, cudaStream_t st);
+
+// Deterministic split reduction of the tcgen05 weight gradients (wgrad_tc.cu): the wgrad launches
+// of one network pass park their per-split partial tiles in a pool and register a slot each;
+// wgrad_reduce() then sums every slot into the parameter gradients with one launch.
+constexpr int kMaxWgradSlots = 16;
+struct WgradReduceSlot {
+  const float* partial;      // [splits][chunks][K + 1][128]
+  float* dW;
+  int64_t lddw;
+  float* dW_hi;              // destination of output rows 128..255 (stacked layers) or nullptr
+  int64_t lddw_hi;
+  float* db;
+  int splits, chunks, K, n_seg;
+  int seg_src[4], seg_len[4], seg_dst[4];
+  int block_begin;           // first block of the reduce grid that works on this slot
+};
+struct WgradReduceList {
+  WgradReduceSlot s[kMaxWgradSlots];
+  int n;
+};
+struct WgradBatch {
+  WgradReduceList list;
+  float* pool;
+  uint64_t pool_floats, used;
+  int blocks;
+};
+// Upper bound of the pool one network pass of the D=8, W=256 architecture needs (floats).
+uint64_t wgrad_pool_floats();
+int wgrad_launch(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                 float* dW_hi, int64_t lddw_hi, float* db, int64_t M, int N, int K, int n_seg,
+                 const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
+                 WgradBatch* batch, void* stream);
+int wgrad_reduce(WgradBatch* batch, cudaStream_t st);
 int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, float* out, int64_t ld_out,
                 cudaStream_t st);
 int scatter_add_rows(const float* src, int64_t ld_src, const int64_t* idx, int64_t R, int dim,

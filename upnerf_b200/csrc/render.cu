@@ -128,6 +128,8 @@ struct Scratch {
   void *dY[8], *dHF, *dG2p, *dG1p, *dQp, *dPE;  // dY[j] = gradient of layer (8-j)'s pre-activation
   float *dssig, *dcsig, *drgb;
   float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
+  float* wg_pool;            // split partials of the tcgen05 weight gradients (bf16 mode)
+  uint64_t wg_pool_floats;
 };
 
 void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool keep, PassBufs* p) {
@@ -235,6 +237,8 @@ void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scr
   s->dCrows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
   s->dWq = b.take<float>(H * W);
   s->dbq = b.take<float>(H);
+  s->wg_pool_floats = es == 2 ? wgrad_pool_floats() : 0;
+  s->wg_pool = s->wg_pool_floats ? b.take<float>(s->wg_pool_floats) : nullptr;
 }
 
 struct Plan {
@@ -285,6 +289,7 @@ struct Ctx {
   int dtype;
   size_t es;
   cudaStream_t st;
+  WgradBatch* wb;  // bf16 backward: weight gradients park split partials here (one reduce per pass)
 };
 
 inline void* col(void* p, int64_t c, size_t es) { return static_cast<uint8_t*>(p) + c * es; }
@@ -312,7 +317,7 @@ int wgrad(const Ctx& c, const void* dY, int64_t lddy, const void* X, int64_t ldx
   if (c.dtype == UPNERF_BF16) {
     int src[4], len[4], dst[4];
     for (int i = 0; i < nseg; ++i) { src[i] = segs[i].src; len[i] = segs[i].len; dst[i] = segs[i].dst; }
-    return upnerf_wgrad_bf16(dY, lddy, X, ldx, dW, lddw, db, M, N, K, nseg, src, len, dst, c.st);
+    return wgrad_launch(dY, lddy, X, ldx, dW, lddw, nullptr, 0, db, M, N, K, nseg, src, len, dst, c.wb, c.st);
   }
   const float* y = static_cast<const float*>(dY);
   const float* x = static_cast<const float*>(X);
@@ -669,8 +674,8 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   const Seg sgW{0, W, 0};
   if (stack) {
     int src = 0, len = W, dst = 0;
-    UPNERF_TRY(upnerf_wgrad2_bf16(s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, dWq_dst, ld_dWq, M, W, 1, &src, &len,
-                                  &dst, c.st));
+    UPNERF_TRY(wgrad_launch(s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, dWq_dst, ld_dWq, nullptr, M, H2, W, 1, &src,
+                            &len, &dst, c.wb, c.st));
     e = ep_none();
     if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
     UPNERF_TRY(linear(c, s.dG1p, H2, k.WcqT, H2, s.dHF, W, M, W, H2, e));
@@ -690,15 +695,6 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
       UPNERF_TRY(linear(c, s.dG1p, H2, k.Wc1T, H2, s.dHF, W, M, W, H, e));
       dhf_live = true;
     }
-  }
-
-  // 4c. rgb head, part 2: chain rule through the folded matrix Wq = W_rgb0[:, :F] W_sf
-  if (ph.rgb && cfg.encode_feat) {
-    UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
-    UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
-    // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
-    UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
-    UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
   }
 
   // 5. xyz_encoding_final + share_sigma  ->  dH8_pre
@@ -770,6 +766,20 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   if (a.d_rays)
     UPNERF_TRY(upnerf_points_posenc_bwd(s.dPE, PEW, a.rays, p.z, R, S, cfg.xyz_L, k.band_xyz, a.d_rays,
                                         c.dtype, c.st));
+
+  // 8. every tcgen05 weight gradient of this pass has parked its split partials: one reduction
+  //    launch sums them (fixed order) into the parameter gradients
+  if (c.wb) UPNERF_TRY(wgrad_reduce(c.wb, c.st));
+
+  // 9. rgb head, part 2 (needs dWq from the reduction): chain rule through the folded matrix
+  //    Wq = W_rgb0[:, :F] W_sf
+  if (ph.rgb && cfg.encode_feat) {
+    UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
+    UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
+    // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
+    UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
+    UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
+  }
   return UPNERF_OK;
 }
 
@@ -807,7 +817,7 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE,
                  "workspace too small: %llu < %llu bytes", (unsigned long long)a->workspace_bytes,
                  (unsigned long long)pl.bytes);
-  Ctx c{a->dtype, pl.es, as_stream(stream)};
+  Ctx c{a->dtype, pl.es, as_stream(stream), nullptr};
   const Phase ph = make_phase(a->cfg, a->sched_mult);
   const int64_t R = a->n_rays;
   const int S = a->n_samples;
@@ -850,7 +860,11 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
   UPNERF_TRY(make_plan(*a, a->workspace, &pl));
   UPNERF_REQUIRE(!a->no_grad, UPNERF_ERR_BAD_CONFIG, "render_bwd: the forward ran with no_grad (nothing was kept)");
   UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE, "workspace too small");
-  Ctx c{a->dtype, pl.es, as_stream(stream)};
+  WgradBatch wb;
+  memset(&wb, 0, sizeof(wb));
+  wb.pool = pl.scratch.wg_pool;
+  wb.pool_floats = pl.scratch.wg_pool_floats;
+  Ctx c{a->dtype, pl.es, as_stream(stream), wb.pool ? &wb : nullptr};
   const Phase ph = make_phase(a->cfg, a->sched_mult);
   if (a->n_importance > 0) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch));
   UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch));
