@@ -379,6 +379,43 @@ uint64_t upnerf_render_workspace_bytes(const upnerf_render_args* a);
 int upnerf_render_fwd(const upnerf_render_args* a, void* stream);
 int upnerf_render_bwd(const upnerf_render_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (f2) Per-ray tail of the train step in ONE launch.
+ * Replaces the monocular-depth affine correction of NeRFSystem.training_step
+ * (models/nerf_system.py:169-177), UPNeRFLoss.forward (losses.py:21-64) together with its
+ * autograd backward, and the psnr of models/nerf_system.py:202-207.  Every gradient is written for
+ * an upstream gradient of 1 (what manual_backward(loss) feeds).  Pointers of terms that are dead in
+ * the phase may be NULL: sched_mult < 1 needs the depth / feature inputs, sched_mult > 0 the colour
+ * ones; t_weight_* NULL = no candidate head; t_beta NULL = no TransientNet.
+ *   losses[0..7] = l_depth_c, l_feat_c, l_rgb_c, l_depth_f, l_feat_f, l_rgb_f, l_beta, l_alpha
+ *                  (0 when absent), losses[8] = their sum in the reference's order,
+ *                  losses[9] = psnr of s_rgb_{fine|coarse} (0 when absent).
+ *   d_depth_scale [n_images,2] is ACCUMULATED (fp32 atomics), all other gradients are overwritten.
+ *   workspace: >= upnerf_tail_workspace_bytes(), zero-filled ONCE by the caller and then reused. */
+#define UPNERF_TAIL_LOSS_SLOTS 16
+typedef struct upnerf_tail_args {
+  int64_t n_rays;
+  int feat_dim;
+  int has_fine;
+  float sched_mult, depth_mult, alpha_reg, near_, far_;
+  const int64_t* img_idx;     /* [R] */
+  const float* inv_depths;    /* [R] */
+  const float* depth_scale;   /* [n_images,2] = (log scale, shift) */
+  const float* rgbs;          /* [R,3] */
+  const float* feats;         /* [R,F] */
+  const float *s_depth_c, *s_depth_f, *t_weight_c, *t_weight_f;   /* [R] */
+  const float *feat_c, *feat_f;                                   /* [R,F] */
+  const float *s_rgb_c, *s_rgb_f;                                 /* [R,3] */
+  const float *t_beta, *t_alpha;                                  /* [R] */
+  float* losses;              /* [UPNERF_TAIL_LOSS_SLOTS] */
+  float *g_s_depth_c, *g_s_depth_f, *g_feat_c, *g_feat_f, *g_s_rgb_c, *g_s_rgb_f, *g_t_beta, *g_t_alpha;
+  float* d_depth_scale;
+  void* workspace;
+  uint64_t workspace_bytes;
+} upnerf_tail_args;
+uint64_t upnerf_tail_workspace_bytes(void);
+int upnerf_tail_loss(const upnerf_tail_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,90 @@ def test_psnr_parity_after_fixed_steps(cuda_dev):
     for which in ("fp32", "bf16"):
         assert abs(psnrs[which][-1] - psnrs["oracle"][-1]) <= 0.1, (which, psnrs[which][-1], psnrs["oracle"][-1])
         assert math.isfinite(psnrs[which][-1])
+
+
+@pytest.mark.parametrize("m", [0.0, 0.37, 1.0])
+@pytest.mark.parametrize("cand", [True, False])
+def test_fused_tail_matches_torch_loss(cuda_dev, m, cand):
+    """upnerf_tail_loss (depth correction + UPNeRFLoss + backward + psnr in one launch) against the
+    torch module `UPNeRFLoss` (reference losses.py:21-64, nerf_system.py:169-177) + autograd."""
+    from upnerf_b200 import _lib as L
+    from upnerf_b200.losses import UPNeRFLoss, fused_tail
+
+    R, F, n_img = 1000, 384, 9
+    g = torch.Generator().manual_seed(int(m * 100) + cand)
+    rnd = lambda *s: torch.rand(*s, generator=g)
+    batch = {"rgbs": rnd(R, 3), "feats": torch.nn.functional.normalize(torch.randn(R, F, generator=g), dim=-1),
+             "img_idx": torch.randint(0, n_img, (R,), generator=g), "inv_depths": 0.05 + 12 * rnd(R)}
+    batch = {k: v.to(cuda_dev) for k, v in batch.items()}
+    ds = (0.3 * torch.randn(n_img, 2, generator=g)).to(cuda_dev).requires_grad_(True)
+    res = {}
+    for typ in ("coarse", "fine"):
+        res[f"s_depth_{typ}"] = (0.1 + 5 * rnd(R)).to(cuda_dev).requires_grad_(True)
+        if m < 1:
+            res[f"feat_{typ}"] = (0.1 * torch.randn(R, F, generator=g)).to(cuda_dev).requires_grad_(True)
+            if cand:
+                res[f"t_weight_{typ}"] = rnd(R).to(cuda_dev).requires_grad_(True)
+        if m > 0:
+            res[f"s_rgb_{typ}"] = rnd(R, 3).to(cuda_dev).requires_grad_(True)
+    if m > 0:
+        res["t_beta"] = (0.1 + rnd(R, 1)).to(cuda_dev).requires_grad_(True)
+        res["t_alpha"] = rnd(R, 1).to(cuda_dev).requires_grad_(True)
+    # torch reference
+    scale, shift = torch.unbind(ds[batch["img_idx"]], 1)
+    inv = batch["inv_depths"] * torch.exp(scale) + shift
+    inv = torch.where(inv < 1 / 5.0, torch.full_like(inv, 1 / 5.0), inv)
+    depth = 1.0 / inv
+    depth = torch.where(depth < 0.1, torch.full_like(depth, 0.1), depth)
+    assert 0 < int((depth == 0.1).sum()) and 0 < int((inv == 0.2).sum())       # both clamps are exercised
+    ref_d = UPNeRFLoss(depth_mult=1e-3, alpha_reg=1.0)(res, batch["rgbs"], batch["feats"], depth, m)
+    ref = sum(ref_d.values())
+    ref.backward()
+    ref_g = {k: v.grad.clone() for k, v in res.items() if v.grad is not None}
+    ref_ds = ds.grad.clone() if ds.grad is not None else torch.zeros_like(ds)
+    ds.grad = torch.zeros_like(ds)
+    ws = torch.zeros(L.tail_workspace_bytes(), device=cuda_dev, dtype=torch.uint8)
+    for rep in range(2):        # second call: the ticket re-arms itself
+        ds.grad.zero_()
+        losses, roots, grads = fused_tail(res, batch, ds, m, depth_mult=1e-3, alpha_reg=1.0, near=0.1, far=5.0,
+                                          fine=True, workspace=ws)
+        torch.cuda.synchronize()
+        got = dict(zip(L.TAIL_TERMS, losses[:8].tolist()))
+        for k, v in ref_d.items():
+            assert abs(got[k] - float(v)) <= 1e-5 * max(1.0, abs(float(v))), (k, got[k], float(v))
+        assert all(got[k] == 0.0 for k in got if k not in ref_d)
+        assert abs(float(losses[8]) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        if m > 0:
+            psnr = -10 * torch.log10(((res["s_rgb_fine"] - batch["rgbs"]) ** 2).mean())
+            assert abs(float(losses[9]) - float(psnr)) <= 1e-4
+        by_id = {id(r): gr for r, gr in zip(roots, grads)}
+        for k, v in res.items():
+            if k in ref_g:
+                assert id(v) in by_id, k
+                err = float((by_id[id(v)] - ref_g[k]).abs().max())
+                assert err <= 1e-6 * max(1.0, float(ref_g[k].abs().max()) * 1e3), (k, err)
+                assert torch.allclose(by_id[id(v)], ref_g[k], rtol=1e-4, atol=1e-9), k
+            else:
+                assert id(v) not in by_id, k      # t_weight is detached in the reference
+        assert torch.allclose(ds.grad, ref_ds, rtol=1e-4, atol=1e-9)
+
+
+def test_training_step_unfused_tail_path(cuda_dev):
+    """`kernel.fused_tail=False` keeps the torch UPNeRFLoss path: same loss and update as the fused one."""
+    R, S, NI, n_img, max_steps = 128, 32, 32, 12, 1000
+    outs = []
+    for fused in (True, False):
+        sys_, cfgs, sd = make_system(n_img, S, NI, "fp32", max_steps, cuda_dev)
+        sys_.hparams["kernel.fused_tail"] = fused
+        sys_.set_progress(0.3)
+        sys_.global_step = 600
+        b = {k: v.to(cuda_dev) for k, v in synth.ray_batch(R, n_img, 100).items()}
+        rng = rng_for(R, S, NI, O.schedule_mult(0.3), 200)
+        l = sys_.training_step(b, 0, rng=rng)
+        outs.append((float(l), sys_.group_main.flat.grad.clone(), sys_.group_pose.flat.grad.clone(),
+                     float(sys_.logged["train/psnr"]), {k: float(v) for k, v in sys_.logged.items() if k.startswith("train/l_")}))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-5 * max(1.0, abs(outs[1][0]))
+    assert abs(outs[0][3] - outs[1][3]) <= 1e-3
+    assert outs[0][4].keys() == outs[1][4].keys()
+    for i in (1, 2):
+        assert float((outs[0][i] - outs[1][i]).norm() / outs[1][i].norm()) <= 1e-4

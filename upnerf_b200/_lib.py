@@ -190,6 +190,33 @@ class RenderArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("no_grad", C.c_int)]
 
 
+_TAIL_IN = ("img_idx", "inv_depths", "depth_scale", "rgbs", "feats", "s_depth_c", "s_depth_f", "t_weight_c",
+            "t_weight_f", "feat_c", "feat_f", "s_rgb_c", "s_rgb_f", "t_beta", "t_alpha")
+_TAIL_OUT = ("losses", "g_s_depth_c", "g_s_depth_f", "g_feat_c", "g_feat_f", "g_s_rgb_c", "g_s_rgb_f", "g_t_beta",
+             "g_t_alpha", "d_depth_scale")
+TAIL_LOSS_SLOTS = 16
+TAIL_TERMS = ("l_depth_c", "l_feat_c", "l_rgb_c", "l_depth_f", "l_feat_f", "l_rgb_f", "l_beta", "l_alpha")
+
+
+class TailArgs(C.Structure):
+    """Mirror of `upnerf_tail_args`."""
+
+    _fields_ = ([("n_rays", C.c_int64), ("feat_dim", C.c_int), ("has_fine", C.c_int), ("sched_mult", C.c_float),
+                 ("depth_mult", C.c_float), ("alpha_reg", C.c_float), ("near_", C.c_float), ("far_", C.c_float)]
+                + [(n, C.c_void_p) for n in _TAIL_IN + _TAIL_OUT]
+                + [("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)])
+
+
+def tail_workspace_bytes() -> int:
+    f = lib().upnerf_tail_workspace_bytes
+    f.restype = C.c_uint64
+    return int(f())
+
+
+def tail_loss(a: TailArgs):
+    check(lib().upnerf_tail_loss(C.byref(a), stream_ptr()), "upnerf_tail_loss")
+
+
 class CompositeArgs(C.Structure):
     _fields_ = ([("R", C.c_int64), ("S", C.c_int), ("cand", C.c_int), ("stat_rgb", C.c_int),
                  ("feat_mode", C.c_int), ("dtype", C.c_int)]

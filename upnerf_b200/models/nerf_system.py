@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
-from ..losses import UPNeRFLoss
+from ..losses import UPNeRFLoss, fused_tail
 from ..utils import ray as ray_utils
 from .nerf import NeRF
 from .rendering import render_rays
@@ -48,6 +48,7 @@ def default_hparams() -> dict:
         "pose.optimize": True, "pose.c2f": (0.1, 0.5), "pose.noise": -1,
         "candidate_schedule": (0.1, 0.5),
         "kernel.precision": "bf16",
+        "kernel.fused_tail": True,      # depth correction + loss + its backward + psnr as one launch (CUDA only)
     }
 
 
@@ -104,6 +105,7 @@ class NeRFSystem(nn.Module):
         self.logged = {}
         self._device = torch.device(device)
         self._progress = 0.0
+        self._tail_ws = None
         self.white_back = False
         if N_images_train is not None:
             self.model_setup(N_images_train)
@@ -203,6 +205,17 @@ class NeRFSystem(nn.Module):
             return 1
         return (1 - math.cos(math.pi * (progress - s) / (e - s))) / 2
 
+    def _live_terms(self, m):
+        """Keys UPNeRFLoss returns in this phase (losses.py:21-64)."""
+        levels = ("c", "f") if self.fine else ("c",)
+        keys = []
+        for tag in levels:
+            if m < 1:
+                keys += [f"l_depth_{tag}", f"l_feat_{tag}"]
+            if m > 0:
+                keys += [f"l_rgb_{tag}"] + (["l_beta", "l_alpha"] if tag == "f" else [])
+        return keys
+
     def set_progress(self, progress: float):
         self._progress = float(progress)
         self.nerf_coarse.progress.data.fill_(self._progress)
@@ -210,8 +223,9 @@ class NeRFSystem(nn.Module):
             self.nerf_fine.progress.data.fill_(self._progress)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, rays, feats, img_idx, sched_mult, train=True, rng=None):
-        """Chunked render + transient blend (models/nerf_system.py:93-148)."""
+    def forward(self, rays, feats, img_idx, sched_mult, train=True, rng=None, blend=True):
+        """Chunked render + transient blend (models/nerf_system.py:93-148).  `blend=False` (the fused
+        training path) skips `rgb_coarse` / `rgb_fine`, which no loss term reads (losses.py:39-64)."""
         hp = self.hparams
         B = rays.shape[0]
         chunk = B if train else hp["val.chunk_size"]
@@ -230,9 +244,10 @@ class NeRFSystem(nn.Module):
         if sched_mult > 0:
             t = self.transient_net(feats, img_idx)
             a, c = t["alpha"], t["rgb"]
-            results["rgb_coarse"] = results["s_rgb_coarse"] * (1 - a.detach()) + c.detach() * a.detach()
-            if self.fine:
-                results["rgb_fine"] = results["s_rgb_fine"] * (1 - a) + c * a
+            if blend:
+                results["rgb_coarse"] = results["s_rgb_coarse"] * (1 - a.detach()) + c.detach() * a.detach()
+                if self.fine:
+                    results["rgb_fine"] = results["s_rgb_fine"] * (1 - a) + c * a
             results["t_beta"], results["t_alpha"] = t["beta"], a
         return results
 
@@ -247,21 +262,45 @@ class NeRFSystem(nn.Module):
         else:
             o, d = ray_utils.get_rays(batch["directions"], batch["c2w"])
             rays = torch.cat([o, d, batch["ray_infos"]], 1)
-        # monocular-depth affine correction (:169-177)
-        scale, shift = torch.unbind(self.depth_scale(img_idx), 1)
-        inv = batch["inv_depths"] * torch.exp(scale) + shift
-        inv = torch.where(inv < 1 / hp["nerf.far"], torch.full_like(inv, 1 / hp["nerf.far"]), inv)
-        depth = 1.0 / inv
-        depth = torch.where(depth < hp["nerf.near"], torch.full_like(depth, hp["nerf.near"]), depth)
-
         sched_mult = self.get_schedule_mult(self._progress)
-        results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng)
-        loss_d = self.loss(results, batch["rgbs"], batch["feats"], depth, sched_mult)
-        loss = sum(loss_d.values())
-
-        self.group_main.zero_grad()
-        self.group_pose.zero_grad()
-        loss.backward()
+        if hp["kernel.fused_tail"] and rays.is_cuda:
+            # render + TransientNet, then ONE launch for the depth correction (:169-177), UPNeRFLoss
+            # (losses.py:21-64), its backward and psnr (:202-207); autograd continues from the
+            # gradients that kernel wrote
+            results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng, blend=False)
+            self.group_main.zero_grad()
+            self.group_pose.zero_grad()
+            if self._tail_ws is None:
+                from .. import _lib as L
+                self._tail_ws = torch.zeros(L.tail_workspace_bytes(), device=rays.device, dtype=torch.uint8)
+            losses, roots, grads = fused_tail(results, batch, self.depth_scale.weight, sched_mult,
+                                              depth_mult=hp["loss.depth_mult"], alpha_reg=hp["loss.alpha_reg"],
+                                              near=hp["nerf.near"], far=hp["nerf.far"], fine=self.fine,
+                                              workspace=self._tail_ws)
+            torch.autograd.backward(roots, grads)
+            from .._lib import TAIL_TERMS
+            live = self._live_terms(sched_mult)
+            loss_d = {k: losses[i] for i, k in enumerate(TAIL_TERMS) if k in live}
+            loss, psnr_ = losses[8], losses[9]
+        else:
+            # monocular-depth affine correction (:169-177)
+            scale, shift = torch.unbind(self.depth_scale(img_idx), 1)
+            inv = batch["inv_depths"] * torch.exp(scale) + shift
+            inv = torch.where(inv < 1 / hp["nerf.far"], torch.full_like(inv, 1 / hp["nerf.far"]), inv)
+            depth = 1.0 / inv
+            depth = torch.where(depth < hp["nerf.near"], torch.full_like(depth, hp["nerf.near"]), depth)
+            results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng)
+            loss_d = self.loss(results, batch["rgbs"], batch["feats"], depth, sched_mult)
+            loss = sum(loss_d.values())
+            self.group_main.zero_grad()
+            self.group_pose.zero_grad()
+            loss.backward()
+            with torch.no_grad():
+                typ = "fine" if self.fine else "coarse"
+                if f"s_rgb_{typ}" in results:
+                    psnr_ = -10 * torch.log10(((results[f"s_rgb_{typ}"] - batch["rgbs"]) ** 2).mean())
+                else:
+                    psnr_ = torch.zeros(1)
         allreduce_mean_(self.group_main.flat.grad)
         if hp["pose.optimize"]:
             allreduce_mean_(self.group_pose.flat.grad)
@@ -269,12 +308,6 @@ class NeRFSystem(nn.Module):
             opt.step()
             sch.step()
 
-        with torch.no_grad():
-            typ = "fine" if self.fine else "coarse"
-            if f"s_rgb_{typ}" in results:
-                psnr_ = -10 * torch.log10(((results[f"s_rgb_{typ}"] - batch["rgbs"]) ** 2).mean())
-            else:
-                psnr_ = torch.zeros(1)
         self.log("train/loss", loss.detach())
         for k, v in loss_d.items():
             self.log(f"train/{k}", v.detach())
