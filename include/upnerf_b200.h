@@ -416,6 +416,30 @@ typedef struct upnerf_tail_args {
 uint64_t upnerf_tail_workspace_bytes(void);
 int upnerf_tail_loss(const upnerf_tail_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (f3) Fused Adam over one flat fp32 buffer.
+ * Replaces torch.optim.Adam.step of the reference's two optimisers (models/nerf_system.py:41-73,
+ * 188-195; utils/optim.py:20-44: Adam(eps 1e-8), no weight decay).  The buffer is a run of
+ * consecutive segments (one per parameter tensor or run of tensors with the same history); a
+ * segment with seg_live = 0 is left untouched -- the reference optimiser skips tensors whose
+ * .grad is None in the current schedule phase -- a live one gets torch's single-tensor update
+ * with its own step_size = lr / (1 - beta1^t) and bc2_sqrt = sqrt(1 - beta2^t). */
+#define UPNERF_ADAM_MAX_SEGMENTS 64
+typedef struct upnerf_adam_args {
+  float* params;             /* [n] updated in place */
+  const float* grads;        /* [n] */
+  float* exp_avg;            /* [n] first moment, updated in place */
+  float* exp_avg_sq;         /* [n] second moment, updated in place */
+  int64_t n;
+  int n_segments;
+  int64_t seg_end[UPNERF_ADAM_MAX_SEGMENTS];      /* exclusive end offsets, ascending, last == n */
+  float seg_step_size[UPNERF_ADAM_MAX_SEGMENTS];
+  float seg_bc2_sqrt[UPNERF_ADAM_MAX_SEGMENTS];
+  int seg_live[UPNERF_ADAM_MAX_SEGMENTS];
+  double beta1, beta2, eps;   /* doubles: 1 - beta is rounded to fp32 from the double, as torch does */
+} upnerf_adam_args;
+int upnerf_adam_step(const upnerf_adam_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

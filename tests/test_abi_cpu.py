@@ -78,3 +78,21 @@ def test_cpu_tensors_are_rejected():
 
     with pytest.raises(L.UpnerfError):
         render_rays({}, {}, torch.zeros(4, 8), torch.zeros(4, dtype=torch.long), 1.0)
+
+
+def test_adam_class_table():
+    from upnerf_b200.models.nerf_system import adam_class
+
+    assert adam_class("nerf_coarse.progress") == "never"
+    assert adam_class("nerf_fine.xyz_encoding_3.0.weight") == "always"
+    assert adam_class("nerf_fine.feat_share_layer.bias") == "always"
+    assert adam_class("nerf_coarse.rgb_share_layer.2.weight") == "rgb"
+    assert adam_class("nerf_coarse.candidate_encoding.0.weight") == "cand"
+    assert adam_class("nerf_coarse.candidate_sigma.0.bias") == "cand"
+    assert adam_class("nerf_coarse.feat_candidate_layer.weight") == "cand"
+    assert adam_class("embedding_fine_a.weight") == "rgb"
+    assert adam_class("embedding_coarse_c.weight") == "cand"
+    assert adam_class("transient_net.rgb_layer.0.weight") == "never"
+    assert adam_class("transient_net.feat_encoder.0.weight") == "rgb"
+    assert adam_class("depth_scale.weight") == "cand"
+    assert adam_class("se3_refine.weight") == "always"

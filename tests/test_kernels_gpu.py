@@ -251,10 +251,11 @@ def _composite_case(R, S, seed):
 
 @pytest.mark.parametrize("mode", ["phase0", "phase1", "phase2", "nocand0"])
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_composite_fwd_bwd_vs_oracle(cuda_dev, mode, dtype):
+@pytest.mark.parametrize("S", [64, 61])      # 61: ragged last 32-sample chunk and load batch
+def test_composite_fwd_bwd_vs_oracle(cuda_dev, mode, dtype, S):
     from upnerf_b200 import _lib as L
 
-    R, S, F = 37, 64, 24
+    R, F = 37, 24
     z, ss, cs, rgb, hf, g2 = _composite_case(R, S, 100)
     tdt = torch.float32 if dtype == "f32" else torch.bfloat16
     code = L.F32 if dtype == "f32" else L.BF16
@@ -395,3 +396,48 @@ def test_get_ray_directions(cuda_dev):
     d = get_ray_directions(6, 8, K)
     assert d.shape == (6, 8, 3)
     assert torch.allclose(d[2, 3], torch.tensor([(3 - 256) / 400.0, -(2 - 192) / 400.0, -1.0]))
+
+
+# ------------------------------------------------------------------ (f3) fused Adam
+def test_flat_adam_matches_per_tensor_torch_adam(cuda_dev):
+    """upnerf_adam_step on one flat buffer with per-class liveness against torch.optim.Adam on the
+    separate tensors, where a dead class has .grad None that step (skipped: no update, no step
+    increment).  Segment boundaries are deliberately not multiples of 4."""
+    from upnerf_b200.optim import FlatAdam
+
+    sizes = [1, 1003, 64, 7, 2050, 5, 129]
+    keys = ["never", "always", "rgb", "rgb", "cand", "always", "cand"]
+    g = torch.Generator().manual_seed(5)
+    init = [torch.randn(n, generator=g) for n in sizes]
+    ref_p = [t.clone().to(cuda_dev).requires_grad_(True) for t in init]
+    ref = torch.optim.Adam(ref_p, lr=3e-3, eps=1e-8, foreach=False, fused=False)
+    flat = torch.nn.Parameter(torch.cat(init).to(cuda_dev))
+    flat.grad = torch.zeros_like(flat)
+    ends, off = [], 0
+    for n, k in zip(sizes, keys):
+        off += n
+        ends.append((off, k))
+    opt = FlatAdam(flat, ends, lr=3e-3, eps=1e-8)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, 0.9)
+    sched_ref = torch.optim.lr_scheduler.ExponentialLR(ref, 0.9)
+    phases = [dict(rgb=False, cand=True), dict(rgb=False, cand=True), dict(rgb=True, cand=True),
+              dict(rgb=True, cand=True), dict(rgb=True, cand=False), dict(rgb=True, cand=False)]
+    for it, ph in enumerate(phases):
+        live = {"always": True, "never": False, **ph}
+        grads = [torch.randn(n, generator=g) * (10.0 ** (it % 3 - 1)) for n in sizes]
+        flat.grad.zero_()
+        off = 0
+        for p_, gr, n, k in zip(ref_p, grads, sizes, keys):
+            p_.grad = gr.to(cuda_dev) if live[k] else None
+            if live[k]:
+                flat.grad[off:off + n] = gr.to(cuda_dev)
+            off += n
+        ref.step()
+        sched_ref.step()
+        opt.set_live(live)
+        opt.step()
+        sched.step()
+        want = torch.cat([p_.detach() for p_ in ref_p])
+        err = float((flat.detach() - want).abs().max())
+        assert err <= 2e-7, (it, err)
+    assert opt.class_steps == {"never": 0, "always": 6, "rgb": 4, "cand": 4}

@@ -217,6 +217,23 @@ def tail_loss(a: TailArgs):
     check(lib().upnerf_tail_loss(C.byref(a), stream_ptr()), "upnerf_tail_loss")
 
 
+ADAM_MAX_SEGMENTS = 64
+
+
+class AdamArgs(C.Structure):
+    """Mirror of `upnerf_adam_args`."""
+
+    _fields_ = [("params", C.c_void_p), ("grads", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64), ("n_segments", C.c_int),
+                ("seg_end", C.c_int64 * ADAM_MAX_SEGMENTS), ("seg_step_size", C.c_float * ADAM_MAX_SEGMENTS),
+                ("seg_bc2_sqrt", C.c_float * ADAM_MAX_SEGMENTS), ("seg_live", C.c_int * ADAM_MAX_SEGMENTS),
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double)]
+
+
+def adam_step(a: AdamArgs):
+    check(lib().upnerf_adam_step(C.byref(a), stream_ptr()), "upnerf_adam_step")
+
+
 class CompositeArgs(C.Structure):
     _fields_ = ([("R", C.c_int64), ("S", C.c_int), ("cand", C.c_int), ("stat_rgb", C.c_int),
                  ("feat_mode", C.c_int), ("dtype", C.c_int)]

@@ -28,6 +28,7 @@ constexpr int kWarps = 4;
 constexpr int kMaxS = 256;
 constexpr int kHF = 256;   // hidden width W
 constexpr int kG2 = 128;   // W / 2
+constexpr int kBatch = 4;  // rows whose loads are in flight together per warp
 
 using CompArgs = upnerf_composite_args;
 
@@ -209,18 +210,27 @@ __global__ void __launch_bounds__(kWarps * 32) composite_fwd_kernel(const CompAr
   float ag[4] = {0.f, 0.f, 0.f, 0.f};
   const T* hf = static_cast<const T*>(p.hf) + r * S * p.ld_hf;
   const T* g2 = p.cand ? static_cast<const T*>(p.g2) + r * S * p.ld_g2 : nullptr;
-  for (int i = 0; i < S; ++i) {
-    const float ws = s_ws[warp][i];
-    float v[8];
-    Vec<T>::template load<8>(hf + i * p.ld_hf, lane, v);
+  // kBatch rows per step, every load issued before the first use: at a few thousand rays the
+  // kernel is bound by bytes in flight per warp, not by bandwidth
+  for (int i0 = 0; i0 < S; i0 += kBatch) {
+    float v[kBatch][8], g[kBatch][4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ah[e] = fmaf(ws, v[e], ah[e]);
-    if (p.cand) {
-      const float wc = s_wc[warp][i];
-      float g[4];
-      Vec<T>::template load<4>(g2 + i * p.ld_g2, lane, g);
+    for (int j = 0; j < kBatch; ++j) {
+      const int i = min(i0 + j, S - 1);
+      Vec<T>::template load<8>(hf + i * p.ld_hf, lane, v[j]);
+      if (p.cand) Vec<T>::template load<4>(g2 + i * p.ld_g2, lane, g[j]);
+    }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) ag[e] = fmaf(wc, g[e], ag[e]);
+    for (int j = 0; j < kBatch; ++j) {
+      const bool ok = i0 + j < S;
+      const float ws = ok ? s_ws[warp][i0 + j] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ah[e] = fmaf(ws, v[j][e], ah[e]);
+      if (p.cand) {
+        const float wc = ok ? s_wc[warp][i0 + j] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ag[e] = fmaf(wc, g[j][e], ag[e]);
+      }
     }
   }
   Vec<float>::store<8>(p.hf_ray + r * kHF, lane, ah);
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(kWarps * 32) composite_fwd_kernel(const CompAr
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const CompArgs p) {
+__global__ void __launch_bounds__(kWarps * 32, 7) composite_bwd_kernel(const CompArgs p) {
   // per-warp scratch: weights, per-sample dots, candidate pre-activation gradient
   __shared__ float s_ws[kWarps][kMaxS];
   __shared__ float s_wc[kWarps][kMaxS];
@@ -249,24 +259,41 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const CompAr
   if (feat) {
     Vec<float>::load<8>(p.g_hf_ray + r * kHF, lane, gh);
     if (p.cand) Vec<float>::load<4>(p.g_g2_ray + r * kG2, lane, gg);
-    for (int i = 0; i < S; ++i) {
-      float v[8];
-      Vec<T>::template load<8>(hf + i * p.ld_hf, lane, v);
-      float d = 0.f;
+    for (int i0 = 0; i0 < S; i0 += kBatch) {
+      float v[kBatch][8], g[kBatch][4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) d = fmaf(v[e], gh[e], d);
-      d = warp_sum(d);
-      float dg = 0.f;
-      if (p.cand) {
-        float g[4];
-        Vec<T>::template load<4>(g2 + i * p.ld_g2, lane, g);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) dg = fmaf(g[e], gg[e], dg);
-        dg = warp_sum(dg);
+      for (int j = 0; j < kBatch; ++j) {
+        const int i = min(i0 + j, S - 1);
+        Vec<T>::template load<8>(hf + i * p.ld_hf, lane, v[j]);
+        if (p.cand) Vec<T>::template load<4>(g2 + i * p.ld_g2, lane, g[j]);
       }
-      if (lane == 0) {
-        s_dh[warp][i] = d;
-        s_dg[warp][i] = dg;
+      float d[kBatch], dg[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        d[j] = 0.f;
+        dg[j] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[j] = fmaf(v[j][e], gh[e], d[j]);
+        if (p.cand) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dg[j] = fmaf(g[j][e], gg[e], dg[j]);
+        }
+      }
+      // kBatch independent butterfly reductions (interleaved by the unroll)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+          d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+          if (p.cand) dg[j] += __shfl_xor_sync(0xffffffffu, dg[j], o);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        if (lane == j && i0 + j < S) {
+          s_dh[warp][i0 + j] = d[j];
+          s_dg[warp][i0 + j] = dg[j];
+        }
       }
     }
     __syncwarp();
@@ -386,20 +413,30 @@ __global__ void __launch_bounds__(kWarps * 32) composite_bwd_kernel(const CompAr
 #pragma unroll
     for (int e = 0; e < 4; ++e) wcs[e] = __ldg(p.w_csigma + lane * 4 + e);
   }
-  for (int i = 0; i < S; ++i) {
-    const float ws = s_ws[warp][i];
-    float o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = ws * gh[e];
-    Vec<T>::template store<8>(dhf + i * p.ld_dhf, lane, o);
+  for (int i0 = 0; i0 < S; i0 += kBatch) {
+    float g[kBatch][4];
     if (p.cand) {
-      const float wc = s_wc[warp][i];
-      const float dcp = s_dg[warp][i];
-      float g[4], q[4];
-      Vec<T>::template load<4>(g2 + i * p.ld_g2, lane, g);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) q[e] = g[e] > 0.f ? (wc * gg[e] + dcp * wcs[e]) : 0.f;
-      Vec<T>::template store<4>(dg2 + i * p.ld_dg2, lane, q);
+      for (int j = 0; j < kBatch; ++j)
+        Vec<T>::template load<4>(g2 + min(i0 + j, S - 1) * p.ld_g2, lane, g[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int i = i0 + j;
+      if (i >= S) break;
+      const float ws = s_ws[warp][i];
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = ws * gh[e];
+      Vec<T>::template store<8>(dhf + i * p.ld_dhf, lane, o);
+      if (p.cand) {
+        const float wc = s_wc[warp][i];
+        const float dcp = s_dg[warp][i];
+        float q[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) q[e] = g[j][e] > 0.f ? (wc * gg[e] + dcp * wcs[e]) : 0.f;
+        Vec<T>::template store<4>(dg2 + i * p.ld_dg2, lane, q);
+      }
     }
   }
 }

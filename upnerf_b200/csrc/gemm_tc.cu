@@ -212,6 +212,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (b >= 0) issue_aux(b);
     }
     uint32_t qg = 0;  // boxes this group has processed (aux barrier phase)
+    // Per-ray bias rows are read with broadcast loads inside the box loop; their first touch
+    // would expose a full L2 round trip per 8 columns, so the lines a warp needs for local tile
+    // `lt` are prefetched into L1 one tile ahead (lanes 0/1 cover the first row's ray, lanes
+    // 30/31 the last row's: a warp of 32 consecutive rows spans at most two rays for S >= 32).
+    auto prefetch_ray_bias = [&](int lt) {
+      if (!ep.ray_bias || (lane > 1 && lane < 30)) return;
+      const int tile = blockIdx.x + lt * gridDim.x;
+      if (tile >= args.num_tiles) return;
+      int64_t row = static_cast<int64_t>(tile) * kBM + row_in_tile;
+      if (row >= args.M) row = args.M - 1;
+      const float* rbp = ep.ray_bias + (row / ep.rows_per_ray) * N + (lane & 1) * 32;
+      for (int ch = (grp - lt * nchunks) & (kGroups - 1); ch < nchunks; ch += kGroups)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rbp + ch * 64));
+    };
+    prefetch_ray_bias(0);
 
     int t = 0;
     for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++t) {
@@ -222,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float r1 = ep.rank1_row ? ep.rank1_row[crow] : 0.f;
       const float* rb = ep.ray_bias ? ep.ray_bias + (crow / ep.rows_per_ray) * N : nullptr;
       float hacc[kMaxHeads] = {0.f, 0.f, 0.f};
+      prefetch_ray_bias(t + 1);
 
       // chunks of this tile owned by this group: first, first + 4, ...
       const int first = (grp - t * nchunks) & (kGroups - 1);
@@ -301,11 +317,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = a[e] > 0.f ? v[e] : 0.f;
             }
-            for (int h = 0; h < nh; ++h) {
-              const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
-              const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
-              hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
-                         v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+            // (fully unrolled with a predicate so that hacc[] stays in registers)
+#pragma unroll
+            for (int h = 0; h < kMaxHeads; ++h) {
+              if (h < nh) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
+                hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
+                           v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+              }
             }
             uint4 out;
             __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&out);
@@ -331,7 +351,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (nh > 0) {
         // row-dot heads: partial sums of the groups are combined by group 0
         float* slot = sHead + ((acc * kGroups + grp) * kBM + row_in_tile) * kMaxHeads;
-        for (int h = 0; h < nh; ++h) slot[h] = hacc[h];
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h < nh) slot[h] = hacc[h];
         named_bar_sync(6, kEpiThreads);
         if (grp == 0 && row_ok) {
           for (int h = 0; h < nh; ++h) {

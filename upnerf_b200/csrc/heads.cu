@@ -60,34 +60,83 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ src, int64_t l
   atomicAdd(table + idx[r] * dim + c, src[r * ld_src + c]);
 }
 
-// out[r, :] = sum over the S samples of ray r of X[r*S + s, :]   (N = 128, one warp per ray)
+// 16 bytes = kVec elements of T per lane
+template <typename T> struct Ld16;
+template <> struct Ld16<float> {
+  static constexpr int kVec = 4;
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Ld16<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(b[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+
+// out[r, :] = sum over the S samples of ray r of X[r*S + s, :]   (N = 128, one warp per ray).
+// A row is 128/kVec lanes of 16 bytes, so a warp covers kRows = 32*kVec/128 rows per load and
+// keeps four such loads in flight.
 template <typename T>
 __global__ void __launch_bounds__(128)
 ray_sum128_kernel(const T* __restrict__ X, int64_t ld, int64_t R, int S, float* __restrict__ out) {
+  constexpr int kVec = Ld16<T>::kVec;
+  constexpr int kLanesPerRow = 128 / kVec;       // 16 (bf16) or 32 (fp32)
+  constexpr int kRows = 32 / kLanesPerRow;       // rows per warp-wide load
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * 4ll + warp;
   if (r >= R) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const T* base = X + r * S * ld + lane * 4;
-  for (int s = 0; s < S; ++s) {
+  const int sub = lane / kLanesPerRow, cl = lane % kLanesPerRow;
+  float acc[kVec];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc[e] += ldv(base + s * ld + e);
+  for (int e = 0; e < kVec; ++e) acc[e] = 0.f;
+  const T* base = X + r * S * ld + cl * kVec;
+  for (int s0 = 0; s0 < S; s0 += 4 * kRows) {
+    float v[4][kVec];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int srow = s0 + j * kRows + sub;
+      Ld16<T>::ld(base + static_cast<int64_t>(srow < S ? srow : S - 1) * ld, v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (s0 + j * kRows + sub < S) {
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) acc[e] += v[j][e];
+      }
+    }
   }
-  float* o = out + r * 128 + lane * 4;
+  if (kRows == 2) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) o[e] = acc[e];
+    for (int e = 0; e < kVec; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+  }
+  if (sub == 0) {
+    float* o = out + r * 128 + cl * kVec;
+#pragma unroll
+    for (int e = 0; e < kVec; e += 4)
+      *reinterpret_cast<float4*>(o + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+  }
 }
 
 // Backward of  rgb = sigmoid(W2 q + b2)  with q = relu(...) (N = 128 hidden units):
 //   d q_pre = (W2^T (d_rgb * rgb (1-rgb))) * (q > 0);  dW2, db2 accumulated;  per-ray sum of
 //   d q_pre -> d_raybias (the per-ray bias of the hidden layer carries direction/appearance).
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 7)
 rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restrict__ rgb,
                     const float* __restrict__ d_rgb, const float* __restrict__ W2, int64_t R, int S,
                     T* __restrict__ dQ, int64_t lddq, float* __restrict__ d_raybias,
                     float* __restrict__ dW2, float* __restrict__ db2) {
-  __shared__ float red[8][3 * 128 + 3];
+  __shared__ float red[4][3 * 128 + 3];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float w2[3][4];
 #pragma unroll
@@ -96,29 +145,38 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
     for (int e = 0; e < 4; ++e) w2[h][e] = W2[h * 128 + lane * 4 + e];
   float aw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float ab[3] = {0.f, 0.f, 0.f};
-  for (int64_t r = blockIdx.x * 8ll + warp; r < R; r += gridDim.x * 8ll) {
+  constexpr int kB = 4;  // samples whose loads are in flight together
+  for (int64_t r = blockIdx.x * 4ll + warp; r < R; r += gridDim.x * 4ll) {
     float rb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int s = 0; s < S; ++s) {
-      const int64_t m = r * S + s;
-      float g[3];
+    for (int s0 = 0; s0 < S; s0 += kB) {
+      float qv[kB][4], g[kB][3];
 #pragma unroll
-      for (int h = 0; h < 3; ++h) {
-        const float y = rgb[m * 3 + h];
-        g[h] = d_rgb[m * 3 + h] * y * (1.f - y);
-        ab[h] += g[h];
-      }
-      float qv[4], d[4];
-      ld4(Q + m * ldq + lane * 4, qv);
+      for (int j = 0; j < kB; ++j) {
+        const int64_t m = r * S + min(s0 + j, S - 1);
+        ld4(Q + m * ldq + lane * 4, qv[j]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        d[e] = qv[e] > 0.f ? (g[0] * w2[0][e] + g[1] * w2[1][e] + g[2] * w2[2][e]) : 0.f;
-        rb[e] += d[e];
-        aw[0][e] += g[0] * qv[e];
-        aw[1][e] += g[1] * qv[e];
-        aw[2][e] += g[2] * qv[e];
+        for (int h = 0; h < 3; ++h) {
+          const float y = __ldg(rgb + m * 3 + h);
+          g[j][h] = __ldg(d_rgb + m * 3 + h) * y * (1.f - y);
+        }
       }
-      st4(dQ + m * lddq + lane * 4, d);
+#pragma unroll
+      for (int j = 0; j < kB; ++j) {
+        if (s0 + j >= S) break;
+        const int64_t m = r * S + s0 + j;
+        float d[4];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) ab[h] += g[j][h];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          d[e] = qv[j][e] > 0.f ? (g[j][0] * w2[0][e] + g[j][1] * w2[1][e] + g[j][2] * w2[2][e]) : 0.f;
+          rb[e] += d[e];
+          aw[0][e] += g[j][0] * qv[j][e];
+          aw[1][e] += g[j][1] * qv[j][e];
+          aw[2][e] += g[j][2] * qv[j][e];
+        }
+        st4(dQ + m * lddq + lane * 4, d);
+      }
     }
     float* o = d_raybias + r * 128 + lane * 4;
 #pragma unroll
@@ -134,10 +192,10 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
     red[warp][386] = ab[2];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 387; i += 256) {
+  for (int i = threadIdx.x; i < 387; i += 128) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][i];
+    for (int w = 0; w < 4; ++w) t += red[w][i];
     if (i < 384) atomicAdd(dW2 + i, t); else atomicAdd(db2 + (i - 384), t);
   }
 }
@@ -175,6 +233,56 @@ rowscale_colsum_kernel(const T* __restrict__ X, int64_t ld, const float* __restr
     atomicAdd(out + 2 * threadIdx.x + 1, t1);
   }
   if (out_s && c2 == 0 && g < groups) atomicAdd(out_s, as);
+}
+
+// Same reduction for rows that are whole 16-byte vectors (N * sizeof(T) % 16 == 0, aligned): a lane
+// owns one 16-byte column chunk, 256 / (lanes per row) rows are read per block-wide load and four
+// such loads are in flight.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowscale_colsum_vec_kernel(const T* __restrict__ X, int64_t ld, const float* __restrict__ s, int64_t M,
+                           int N, float* __restrict__ out, float* __restrict__ out_s) {
+  constexpr int kVec = Ld16<T>::kVec;
+  __shared__ float red[256][kVec + 1];
+  const int lpr = N / kVec;                 // lanes per row (power of two, <= 64)
+  const int rpb = 256 / lpr;                // rows per block-wide load
+  const int g = threadIdx.x / lpr, cl = threadIdx.x % lpr;
+  float acc[kVec];
+#pragma unroll
+  for (int e = 0; e < kVec; ++e) acc[e] = 0.f;
+  float as = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * rpb;
+  for (int64_t m0 = blockIdx.x * static_cast<int64_t>(rpb) + g; m0 < M; m0 += 4 * stride) {
+    float v[4][kVec], sv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t m = m0 + j * stride;
+      const int64_t mc = m < M ? m : M - 1;
+      Ld16<T>::ld(X + mc * ld + cl * kVec, v[j]);
+      sv[j] = m < M ? (s ? __ldg(s + mc) : 1.f) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < kVec; ++e) acc[e] = fmaf(sv[j], v[j][e], acc[e]);
+      as += sv[j];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < kVec; ++e) red[threadIdx.x][e] = acc[e];
+  red[threadIdx.x][kVec] = as;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    const int c = threadIdx.x / kVec, e = threadIdx.x % kVec;
+    float t = 0.f;
+    for (int k = 0; k < rpb; ++k) t += red[k * lpr + c][e];
+    atomicAdd(out + threadIdx.x, t);
+  }
+  if (out_s && threadIdx.x == 255) {
+    float t = 0.f;
+    for (int k = 0; k < rpb; ++k) t += red[k * lpr][kVec];
+    atomicAdd(out_s, t);
+  }
 }
 
 // fp32-mode row-dot heads: out[m,h] = act(X[m,:] . w[h,:] + b[h]); one warp per row.
@@ -247,16 +355,16 @@ int ray_sum128(const void* X, int64_t ld, int64_t R, int S, float* out, int dtyp
 int rgb_head_bwd(const void* Q, int64_t ldq, const float* rgb, const float* d_rgb, const float* W2,
                  int64_t R, int S, void* dQ, int64_t lddq, float* d_raybias, float* dW2, float* db2,
                  int dtype, cudaStream_t st) {
-  int64_t blocks = ceil_div64(R, 8);
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  int64_t blocks = ceil_div64(R, 4);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 7;
   if (blocks > cap) blocks = cap;
   LaunchScope scope(kCatHeads, st);
   if (dtype == UPNERF_BF16)
-    rgb_head_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    rgb_head_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
         static_cast<const __nv_bfloat16*>(Q), ldq, rgb, d_rgb, W2, R, S, static_cast<__nv_bfloat16*>(dQ),
         lddq, d_raybias, dW2, db2);
   else
-    rgb_head_bwd_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+    rgb_head_bwd_kernel<float><<<static_cast<unsigned>(blocks), 128, 0, st>>>(
         static_cast<const float*>(Q), ldq, rgb, d_rgb, W2, R, S, static_cast<float*>(dQ), lddq,
         d_raybias, dW2, db2);
   UPNERF_CHECK_LAUNCH("rgb_head_bwd_kernel");
@@ -276,6 +384,28 @@ int rowscale_colsum(const void* X, int64_t ld, const float* s, int64_t M, int N,
   }
   UPNERF_REQUIRE(N >= 2 && N <= 256 && N % 2 == 0 && 256 % (N / 2) == 0, UPNERF_ERR_BAD_SHAPE,
                  "rowscale_colsum: N=%d", N);
+  {
+    const size_t es = dtype == UPNERF_BF16 ? 2 : 4;
+    const int kvec = static_cast<int>(16 / es);
+    const int lpr = N / kvec;
+    if (N % kvec == 0 && lpr >= 1 && lpr <= 64 && (lpr & (lpr - 1)) == 0 && (ld * es) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(X) % 16 == 0) {
+      const int rpb = 256 / lpr;
+      int64_t blocks = ceil_div64(M, static_cast<int64_t>(rpb) * 4);
+      const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+      if (blocks > cap) blocks = cap;
+      if (blocks < 1) blocks = 1;
+      LaunchScope scope(kCatHeads, st);
+      if (dtype == UPNERF_BF16)
+        rowscale_colsum_vec_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(X), ld, s, M, N, out, out_s);
+      else
+        rowscale_colsum_vec_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+            static_cast<const float*>(X), ld, s, M, N, out, out_s);
+      UPNERF_CHECK_LAUNCH("rowscale_colsum_vec_kernel");
+      return UPNERF_OK;
+    }
+  }
   const int groups = 256 / (N / 2);
   int64_t blocks = ceil_div64(M, groups * 8);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;

@@ -189,6 +189,94 @@ points_posenc_bwd_kernel(const T* __restrict__ d_pe, int64_t ld_row, const float
   }
 }
 
+// Same, for rows that are exactly 64 elements wide and 16-byte aligned (the skip-buffer layout,
+// 3 + 6L <= 64): a lane fetches its whole gradient row with 16-byte loads before the trigonometry
+// instead of 63 scattered element loads.  L is a template parameter so the row stays in registers.
+template <typename T, int L>
+__global__ void __launch_bounds__(128)
+points_posenc_bwd_row_kernel(const T* __restrict__ d_pe, int64_t ld_row, const float* __restrict__ rays,
+                             const float* __restrict__ z, int64_t R, int S,
+                             const float* __restrict__ band_w, float* __restrict__ d_rays) {
+  static_assert(3 + 6 * L <= 64, "row does not fit the 64-wide layout");
+  __shared__ float bw[kMaxL];
+  if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
+  __syncthreads();
+  // one warp per (ray, 32-sample chunk): four times the warps of a warp-per-ray mapping, so a
+  // few thousand rays still fill the machine evenly; the per-ray sum finishes with atomics
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpr = (S + 31) >> 5;
+  const int64_t q = blockIdx.x * 4ll + warp;
+  if (q >= R * cpr) return;
+  const int64_t r = q / cpr;
+  const int s = static_cast<int>(q - r * cpr) * 32 + lane;
+  const float kPi = 3.14159265358979323846f;
+  const float* ray = rays + r * 8;
+  float o3[3], d3[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o3[c] = ray[c];
+    d3[c] = ray[3 + c];
+  }
+  float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+  if (s < S) {
+    const int64_t m = r * S + s;
+    const float zz = z[m];
+    float g[64];
+    if constexpr (sizeof(T) == 2) {
+      const uint4* src = reinterpret_cast<const uint4*>(d_pe + m * ld_row);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const uint4 t = __ldg(src + v);
+        const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(b[i]);
+          g[v * 8 + 2 * i] = f.x;
+          g[v * 8 + 2 * i + 1] = f.y;
+        }
+      }
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(d_pe + m * ld_row);
+#pragma unroll
+      for (int v = 0; v < 16; ++v) {
+        const float4 t = __ldg(src + v);
+        g[v * 4] = t.x; g[v * 4 + 1] = t.y; g[v * 4 + 2] = t.z; g[v * 4 + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xc = __fadd_rn(o3[c], __fmul_rn(d3[c], zz));
+      float dx = g[c];
+      float f = kPi;
+#pragma unroll
+      for (int k = 0; k < L; ++k) {
+        float sn, cs;
+        sincosf(__fmul_rn(xc, f), &sn, &cs);
+        dx += bw[k] * f * (cs * g[3 + c * 2 * L + k] - sn * g[3 + c * 2 * L + L + k]);
+        f *= 2.f;
+      }
+      go[c] += dx;
+      gd[c] += dx * zz;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      go[c] += __shfl_xor_sync(0xffffffffu, go[c], o);
+      gd[c] += __shfl_xor_sync(0xffffffffu, gd[c], o);
+    }
+  }
+  if (lane == 0) {
+    float* out = d_rays + r * 8;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(out + c, go[c]);
+      atomicAdd(out + 3 + c, gd[c]);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace upnerf
 
@@ -261,6 +349,18 @@ int upnerf_points_posenc_bwd(const void* d_pe, int64_t ld_pe, const float* rays,
                  "points_posenc_bwd: bad sizes");
   const unsigned grid = static_cast<unsigned>(ceil_div64(n_rays, 4));
   LaunchScope scope(kCatPosenc, as_stream(stream));
+  const size_t es = dtype == UPNERF_BF16 ? 2 : 4;
+  if (L == 10 && ld_pe >= 64 && (ld_pe * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(d_pe) & 15) == 0) {
+    const unsigned grid = static_cast<unsigned>(ceil_div64(n_rays * ((n_samples + 31) / 32), 4));
+    if (dtype == UPNERF_BF16)
+      points_posenc_bwd_row_kernel<__nv_bfloat16, 10><<<grid, 128, 0, as_stream(stream)>>>(
+          static_cast<const __nv_bfloat16*>(d_pe), ld_pe, rays, z, n_rays, n_samples, band_w, d_rays);
+    else
+      points_posenc_bwd_row_kernel<float, 10><<<grid, 128, 0, as_stream(stream)>>>(
+          static_cast<const float*>(d_pe), ld_pe, rays, z, n_rays, n_samples, band_w, d_rays);
+    UPNERF_CHECK_LAUNCH("points_posenc_bwd_row_kernel");
+    return UPNERF_OK;
+  }
   if (dtype == UPNERF_BF16)
     points_posenc_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(
         static_cast<const __nv_bfloat16*>(d_pe), ld_pe, rays, z, n_rays, n_samples, L, band_w, d_rays);

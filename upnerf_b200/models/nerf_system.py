@@ -23,6 +23,7 @@ import torch.distributed as dist
 from torch import nn
 
 from ..losses import UPNeRFLoss, fused_tail
+from ..optim import FlatAdam
 from ..utils import ray as ray_utils
 from .nerf import NeRF
 from .rendering import render_rays
@@ -55,8 +56,9 @@ def default_hparams() -> dict:
 class FlatGroup:
     """Parameters re-homed as views of one flat fp32 buffer, gradients likewise."""
 
-    def __init__(self, params, device):
+    def __init__(self, params, device, keys=None):
         self.params = list(params)
+        self.keys = list(keys) if keys is not None else ["always"] * len(self.params)
         n = sum(p.numel() for p in self.params)
         self.flat = nn.Parameter(torch.empty(n, device=device, dtype=torch.float32))
         self.flat.grad = torch.zeros(n, device=device, dtype=torch.float32)
@@ -74,12 +76,44 @@ class FlatGroup:
     def zero_grad(self):
         self.flat.grad.zero_()
 
+    def segments(self):
+        """[(end_offset, class_key)] runs covering the buffer (the FlatAdam segment table)."""
+        return [(self.offsets[id(p)][0] + self.offsets[id(p)][1], k) for p, k in zip(self.params, self.keys)]
+
+    def grad_of(self, params):
+        """The slice of the flat GRADIENT buffer covering a run of consecutive parameters."""
+        params = list(params)
+        a = self.offsets[id(params[0])][0]
+        o, k = self.offsets[id(params[-1])]
+        return self.flat.grad[a:o + k]
+
     def slice_of(self, params):
         """Getter of the autograd-visible slice of the flat leaf covering a run of consecutive parameters."""
         params = list(params)
         a = self.offsets[id(params[0])][0]
         o, k = self.offsets[id(params[-1])]
         return lambda: self.flat[a:o + k]
+
+
+def adam_class(name: str) -> str:
+    """Which schedule phases put a parameter into the loss graph (= give it a non-None .grad in the
+    reference, models/nerf.py:80-124, models/nerf_system.py:128-144, losses.py:21-64):
+    "rgb" = sched_mult > 0, "cand" = sched_mult < 1, "never" (progress; TransientNet.rgb_layer only
+    feeds rgb_fine, which no loss term reads), "always"."""
+    head = name.split(".")[0]
+    if name.endswith("progress"):
+        return "never"
+    if head == "transient_net":
+        return "never" if ".rgb_layer." in name else "rgb"
+    if head.startswith("embedding_"):
+        return "rgb" if head.endswith("_a") else "cand"
+    if head == "depth_scale":
+        return "cand"
+    if ".rgb_share_layer." in name:
+        return "rgb"
+    if ".candidate_" in name or ".feat_candidate_layer." in name or ".rgb_candidate_layer." in name:
+        return "cand"
+    return "always"
 
 
 def allreduce_mean_(t: torch.Tensor) -> None:
@@ -143,15 +177,25 @@ class NeRFSystem(nn.Module):
         nn.init.zeros_(self.depth_scale.weight)
         self.to(self._device)
         # flat buffers: group 0 = reference optimizer 0 (networks + embeddings), group 1 = pose
-        main = []
-        for m in self.models.values():
-            main += list(m.parameters())
-        for e in self.embeddings.values():
+        main, keys = [], []
+        for mname, m in self.models.items():
+            attr = {"nerf_coarse": "nerf_coarse", "nerf_fine": "nerf_fine", "transient_network": "transient_net"}[mname]
+            for pname, p in m.named_parameters():
+                main.append(p)
+                keys.append(adam_class(f"{attr}.{pname}"))
+        for ename, e in self.embeddings.items():
             main += list(e.parameters())
-        self.group_main = FlatGroup(main, self._device)
-        self.group_pose = FlatGroup([self.depth_scale.weight, self.se3_refine.weight], self._device)
-        for m in (self.nerf_coarse, *( [self.nerf_fine] if self.fine else [])):
+            keys.append(adam_class(f"embedding_{ename}.weight"))
+        self.group_main = FlatGroup(main, self._device, keys)
+        self.group_pose = FlatGroup([self.depth_scale.weight, self.se3_refine.weight], self._device,
+                                    [adam_class("depth_scale.weight"), adam_class("se3_refine.weight")])
+        # the render backward accumulates straight into these slices of the flat gradient buffer
+        self._grad_sinks = {}
+        for which, m in (("coarse", self.nerf_coarse), *((("fine", self.nerf_fine),) if self.fine else ())):
             m._upnerf_flat = self.group_main.slice_of(m.parameters())
+            self._grad_sinks[which] = self.group_main.grad_of(m.parameters())
+        for ename, e in self.embeddings.items():
+            self._grad_sinks[ename] = self.group_main.grad_of([e.weight])
 
     def load_state_dict(self, sd, strict=True):
         # parameters are views of the flat buffers: copy in place so the views stay valid
@@ -171,17 +215,20 @@ class NeRFSystem(nn.Module):
         hp = self.hparams
         fused = self._device.type == "cuda"
 
-        def make(prefix, flat):
+        def make(prefix, group):
             if hp[f"{prefix}.type"] != "adam":
                 raise NotImplementedError(hp[f"{prefix}.type"])
-            opt = torch.optim.Adam([flat], lr=hp[f"{prefix}.lr"], eps=1e-8, fused=fused)
+            if fused:      # one upnerf_adam_step launch, per-segment liveness like the per-tensor reference
+                opt = FlatAdam(group.flat, group.segments(), lr=hp[f"{prefix}.lr"], eps=1e-8)
+            else:
+                opt = torch.optim.Adam([group.flat], lr=hp[f"{prefix}.lr"], eps=1e-8)
             gamma = (hp[f"{prefix}.scheduler.lr_end"] / hp[f"{prefix}.lr"]) ** (1.0 / hp["max_steps"])
             return opt, torch.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma)
 
-        self.optimizer, self.scheduler = make("optimizer", self.group_main.flat)
+        self.optimizer, self.scheduler = make("optimizer", self.group_main)
         self._optimizers, self._schedulers = [self.optimizer], [self.scheduler]
         if hp["pose.optimize"]:
-            self.optimizer_pose, self.scheduler_pose = make("optimizer_pose", self.group_pose.flat)
+            self.optimizer_pose, self.scheduler_pose = make("optimizer_pose", self.group_pose)
             self._optimizers.append(self.optimizer_pose)
             self._schedulers.append(self.scheduler_pose)
         return self._optimizers, self._schedulers
@@ -237,7 +284,8 @@ class NeRFSystem(nn.Module):
                                N_samples=hp["nerf.N_samples"], use_disp=hp["nerf.use_disp"],
                                perturb=hp["nerf.perturb"] if train else 0, N_importance=hp["nerf.N_importance"],
                                white_back=self.white_back, encode_feat=hp["nerf.feat_dim"] > 0,
-                               validation=not train, precision=hp["kernel.precision"], rng=rng)
+                               validation=not train, precision=hp["kernel.precision"], rng=rng,
+                               grad_sink=self._grad_sinks if (train and B == chunk) else None)
             for k, v in part.items():
                 results[k].append(v)
         results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
@@ -304,7 +352,11 @@ class NeRFSystem(nn.Module):
         allreduce_mean_(self.group_main.flat.grad)
         if hp["pose.optimize"]:
             allreduce_mean_(self.group_pose.flat.grad)
+        live = {"always": True, "never": False, "rgb": sched_mult > 0 or hp["nerf.feat_dim"] <= 0,
+                "cand": sched_mult < 1}
         for opt, sch in zip(self._optimizers, self._schedulers):
+            if isinstance(opt, FlatAdam):
+                opt.set_live(live)
             opt.step()
             sch.step()
 

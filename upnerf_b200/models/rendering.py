@@ -8,7 +8,9 @@ fallback -- CPU tensors raise.
 
 Extra keyword arguments (ours): `precision="bf16"|"fp32"` (default: $UPNERF_PRECISION or
 "bf16") and `rng=dict(perturb_rand=Tensor[R,S], u=[Tensor[R,n0], Tensor[R,n1]])` to inject the
-uniforms the reference would draw for parity tests.
+uniforms the reference would draw for parity tests; `grad_sink=dict(coarse=, fine=,
+coarse_a=, ...)` names fp32 buffers the backward ACCUMULATES parameter / embedding gradients into
+(slices of a flat .grad buffer) instead of returning fresh tensors to autograd.
 """
 from __future__ import annotations
 
@@ -137,15 +139,29 @@ class _RenderFn(torch.autograd.Function):
         d_rays = torch.zeros_like(rays) if need[1] else None
         a.d_rays = L._vp(d_rays)
         grads = {}
+        sink = meta.get("grad_sink") or {}
+
+        def dest(key, like):
+            """Gradient destination: the caller's accumulation buffer (`grad_sink`, e.g. a slice of
+            a flat .grad buffer -- the kernels ACCUMULATE, so autograd gets None for that input) or
+            a fresh zero tensor handed back to autograd."""
+            if like is None:
+                return None
+            t = sink.get(key)
+            if t is not None:
+                if t.numel() != like.numel() or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise L.UpnerfError(f"render_rays: grad_sink[{key!r}] does not match its parameter")
+                hold.append(t)
+                return t
+            grads[key] = torch.zeros_like(like)
+            return grads[key]
+
         for which, flat, ea, ec in (("coarse", flat_c, emb_ca, emb_cc), ("fine", flat_f, emb_fa, emb_fc)):
             if flat is None:
                 continue
             io = getattr(a, which)
-            grads[which] = torch.zeros_like(flat)
-            io.d_params = grads[which].data_ptr()
-            grads[which + "_a"] = torch.zeros_like(ea) if ea is not None else None
-            grads[which + "_c"] = torch.zeros_like(ec) if ec is not None else None
-            io.d_emb_a, io.d_emb_c = L._vp(grads[which + "_a"]), L._vp(grads[which + "_c"])
+            io.d_params = dest(which, flat).data_ptr()
+            io.d_emb_a, io.d_emb_c = L._vp(dest(which + "_a", ea)), L._vp(dest(which + "_c", ec))
         L.render_bwd(a)
         return (None, d_rays, grads.get("coarse"), grads.get("fine"), grads.get("coarse_a"),
                 grads.get("fine_a"), grads.get("coarse_c"), grads.get("fine_c"))
@@ -187,7 +203,7 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
                 sched_mult=m, use_disp=use_disp, perturb=perturb, keys=_phase_keys(cfg, m),
                 img_idx=img_idx.contiguous().long(), perturb_rand=as_f32(perturb_rand), u0=as_f32(u0),
                 u1=as_f32(u1), dtype=_dtype_code(kwargs.get("precision") or default_precision()),
-                n_images=0, no_grad=False)
+                n_images=0, no_grad=False, grad_sink=kwargs.get("grad_sink"))
     emb = lambda k: embeddings[k].weight if k in embeddings else None
     ea_c = emb("coarse_a") if coarse.encode_appearance else None
     ec_c = emb("coarse_c") if coarse.encode_candidate else None
