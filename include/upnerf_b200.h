@@ -437,6 +437,8 @@ typedef struct upnerf_adam_args {
   float seg_bc2_sqrt[UPNERF_ADAM_MAX_SEGMENTS];
   int seg_live[UPNERF_ADAM_MAX_SEGMENTS];
   double beta1, beta2, eps;   /* doubles: 1 - beta is rounded to fp32 from the double, as torch does */
+  double decay_mul;           /* AdamW (tto, models/nerf_system_optmize.py:61): params *= 1 - lr*weight_decay
+                                 before the update, as torch.optim.AdamW does; 0 or 1 = plain Adam */
 } upnerf_adam_args;
 int upnerf_adam_step(const upnerf_adam_args* a, void* stream);
 

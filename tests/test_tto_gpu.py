@@ -1,0 +1,114 @@
+"""GPU: NeRFSystemOptimize (test-time optimisation, reference models/nerf_system_optmize.py:48-169)
+against the same step restated with the CPU oracle (oracle/train_step.py:OracleOptimize): loss,
+the appearance-table / pose updates of both optimiser set-ups, frozen networks, and the chunked
+no-grad validation render."""
+import pytest
+import torch
+
+from oracle import synth
+from oracle import upnerf_oracle as O
+from oracle.train_step import KW, OracleOptimize, rng_for
+
+pytestmark = pytest.mark.gpu
+
+
+def make(n_img, S, NI, precision, pose_optimize, device, seed=21, chunk=4096):
+    from upnerf_b200.models.nerf_system_optmize import NeRFSystemOptimize
+
+    cfgs = {"nerf_coarse": O.NerfConfig(typ="coarse", **KW), "nerf_fine": O.NerfConfig(typ="fine", **KW)}
+    sd = {}
+    for k, cfg in cfgs.items():
+        for pn, v in synth.nerf_state(cfg, seed + (k == "nerf_fine"), progress=0.9).items():
+            sd[f"{k}.{pn}"] = v
+    for k, v in synth.embeddings(n_img, cfgs["nerf_coarse"], seed).items():
+        sd[f"embedding_{k}.weight"] = v * 0.3
+    for pn, v in synth.transient_state(n_img, seed).items():
+        sd[f"transient_net.{pn}"] = v
+    sd["se3_refine.weight"] = synth.uniform((n_img, 6), seed + 5, -0.02, 0.02)
+    sd["depth_scale.weight"] = torch.zeros(n_img, 2)
+    hp = {"nerf.N_samples": S, "nerf.N_importance": NI, "kernel.precision": precision, "pose_optimize": pose_optimize,
+          "val.chunk_size": chunk}
+    torch.manual_seed(0)
+    # the checkpoint supplies the two NeRFs (utils/__init__.py:23-27); the rest is set below
+    ckpt = {"state_dict": {k: v for k, v in sd.items() if k.startswith("nerf_")}}
+    sys_ = NeRFSystemOptimize(hp, N_images_train=n_img, N_images_test=n_img, checkpoint=ckpt, device=device)
+    own = sys_.state_dict()
+    for k in ("nerf_coarse.xyz_encoding_3.0.weight", "nerf_fine.rgb_share_layer.2.bias", "nerf_fine.progress"):
+        assert torch.equal(own[k].cpu(), sd[k]), k                     # the checkpoint really was loaded
+    sys_.load_state_dict(sd)
+    return sys_, cfgs, sd
+
+
+@pytest.mark.parametrize("pose_optimize", [False, True])
+def test_tto_step_matches_oracle_fp32(cuda_dev, pose_optimize):
+    R, S, NI, n_img = 128, 32, 32, 6
+    sys_, cfgs, sd = make(n_img, S, NI, "fp32", pose_optimize, cuda_dev)
+    orc = OracleOptimize(cfgs, sd, S, NI, pose_optimize)
+    assert not sys_.nerf_fine.encode_candidate and not sys_.nerf_coarse.encode_candidate
+    for it in range(3):
+        b = synth.ray_batch(R, n_img, 500 + it)
+        rng = rng_for(R, S, NI, 1, 600 + 10 * it)
+        l_ref, _ = orc.step(b, rng)
+        l = sys_.training_step({k: v.to(cuda_dev) for k, v in b.items()}, it, rng=rng)
+        assert abs(float(l) - float(l_ref)) <= 1e-4 * max(1.0, abs(float(l_ref))), (it, float(l), float(l_ref))
+    own = sys_.state_dict()
+    trained = ["embedding_fine_a.weight"] + (["se3_refine.weight"] if pose_optimize else [])
+    for k, v in orc.p.items():
+        upd_ref = v.detach() - sd[k]
+        upd = own[k].cpu() - sd[k]
+        if k in trained:
+            assert float(upd_ref.abs().max()) > 0, k
+            # Adam-type first steps are ~lr*sign(g): compare norm-wise (see test_train_step_gpu.py)
+            r = float((upd - upd_ref).norm() / upd_ref.norm())
+            assert r <= 0.1, (k, r)
+        else:
+            assert float(upd.abs().max()) == 0, k                      # everything else is frozen
+    psnr = float(sys_.logged["train/psnr"])
+    assert abs(psnr - float(-10 * torch.log10(l_ref))) <= 1e-2
+
+
+def test_tto_adamw_decay_matches_torch(cuda_dev):
+    """FlatAdam(weight_decay) == torch.optim.AdamW on the same gradients (utils/optim.py:29)."""
+    from upnerf_b200.optim import FlatAdam
+
+    g = torch.Generator().manual_seed(3)
+    w0 = torch.randn(999, generator=g)
+    p_ref = w0.clone().requires_grad_(True)
+    ref = torch.optim.AdamW([p_ref], lr=1e-1)
+    flat = torch.nn.Parameter(w0.clone().to(cuda_dev))
+    flat.grad = torch.zeros_like(flat)
+    opt = FlatAdam(flat, [(999, "always")], lr=1e-1, eps=1e-8, weight_decay=1e-2)
+    for _ in range(5):
+        gr = torch.randn(999, generator=g)
+        p_ref.grad = gr.clone()
+        ref.step()
+        flat.grad.copy_(gr)
+        opt.step()
+    assert float((flat.detach().cpu() - p_ref.detach()).abs().max()) <= 2e-6
+
+
+def test_tto_step_bf16_and_validation(cuda_dev):
+    R, S, NI, n_img = 256, 32, 32, 6
+    sys_, cfgs, sd = make(n_img, S, NI, "bf16", True, cuda_dev, chunk=96)
+    orc = OracleOptimize(cfgs, sd, S, NI, True)
+    b = synth.ray_batch(R, n_img, 700)
+    rng = rng_for(R, S, NI, 1, 710)
+    l_ref, _ = orc.step(b, rng)
+    l = sys_.training_step({k: v.to(cuda_dev) for k, v in b.items()}, 0, rng=rng)
+    assert abs(float(l) - float(l_ref)) <= 2e-2 * max(1.0, abs(float(l_ref)))
+    for k in ("embedding_fine_a.weight", "se3_refine.weight"):
+        assert float((sys_.state_dict()[k].cpu() - sd[k]).abs().max()) > 0, k
+    # validation: one image = one pose for all rays, deterministic sampling, chunks of 96 rays
+    sys32, _, _ = make(n_img, S, NI, "fp32", False, cuda_dev, chunk=96)
+    orc32 = OracleOptimize(cfgs, sd, S, NI, False)
+    vb = synth.ray_batch(R, n_img, 720)
+    vb["img_idx"] = torch.full((R,), 2, dtype=torch.long)
+    vb["c2w"] = vb["c2w"][0]
+    with torch.no_grad():
+        ref = orc32.render({**vb, "c2w": vb["c2w"][None].expand(R, 3, 4)}, None, 0.0)
+    batch = {k: v.to(cuda_dev)[None] for k, v in vb.items()}        # DataLoader(batch_size=1) layout
+    out = sys32.validation_step(batch, 0)
+    assert float((out["s_rgb"].cpu() - ref["s_rgb_fine"]).abs().max()) <= 1e-4
+    mse = ((ref["s_rgb_fine"] - vb["rgbs"]) ** 2).mean()
+    assert abs(float(out["psnr"]) - float(-10 * torch.log10(mse))) <= 1e-3
+    assert float(sys32.best_psnr) == float(out["psnr"])

@@ -227,7 +227,7 @@ class AdamArgs(C.Structure):
                 ("n", C.c_int64), ("n_segments", C.c_int),
                 ("seg_end", C.c_int64 * ADAM_MAX_SEGMENTS), ("seg_step_size", C.c_float * ADAM_MAX_SEGMENTS),
                 ("seg_bc2_sqrt", C.c_float * ADAM_MAX_SEGMENTS), ("seg_live", C.c_int * ADAM_MAX_SEGMENTS),
-                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double)]
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("decay_mul", C.c_double)]
 
 
 def adam_step(a: AdamArgs):

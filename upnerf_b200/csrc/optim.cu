@@ -29,11 +29,13 @@ __device__ __forceinline__ int find_segment(const upnerf_adam_args& a, int64_t i
 
 struct Betas {
   float b2, om1, om2, eps;   // beta2, fp32(1 - beta1), fp32(1 - beta2) (rounded from double like torch), eps
+  float decay;               // AdamW: param.mul_(1 - lr * weight_decay) first; 1 = plain Adam
 };
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const Betas& k,
                                          float step_size, float bc2_sqrt) {
   const float eps = k.eps;
+  p = p * k.decay;
   m = m + (g - m) * k.om1;                            // exp_avg.lerp_(grad, 1 - beta1)
   v = __fmaf_rn(k.om2, g * g, v * k.b2);              // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
   const float denom = __fdiv_rn(__fsqrt_rn(v), bc2_sqrt) + eps;
@@ -89,7 +91,8 @@ extern "C" int upnerf_adam_step(const upnerf_adam_args* a, void* stream) {
   const unsigned grid = static_cast<unsigned>(ceil_div64(ceil_div64(a->n, 4), 256));
   LaunchScope scope(kCatHeads, as_stream(stream), 0.0, 28.0 * a->n);
   const Betas k{static_cast<float>(a->beta2), static_cast<float>(1.0 - a->beta1), static_cast<float>(1.0 - a->beta2),
-                static_cast<float>(a->eps)};
+                static_cast<float>(a->eps),
+                (a->decay_mul == 0.0) ? 1.f : static_cast<float>(a->decay_mul)};
   adam_kernel<<<grid, 256, 0, as_stream(stream)>>>(*a, k);
   UPNERF_CHECK_LAUNCH("adam_kernel");
   return UPNERF_OK;

@@ -128,6 +128,7 @@ struct Scratch {
   void *dY[8], *dHF, *dG2p, *dG1p, *dQp, *dPE;  // dY[j] = gradient of layer (8-j)'s pre-activation
   float *dssig, *dcsig, *drgb;
   float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
+  float* gdump;              // sink of the tiny side-effect gradients when the weights are frozen
   float* wg_pool;            // split partials of the tcgen05 weight gradients (bf16 mode)
   uint64_t wg_pool_floats;
 };
@@ -237,6 +238,7 @@ void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scr
   s->dCrows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
   s->dWq = b.take<float>(H * W);
   s->dbq = b.take<float>(H);
+  s->gdump = b.take<float>(4 * H);
   s->wg_pool_floats = es == 2 ? wgrad_pool_floats() : 0;
   s->wg_pool = s->wg_pool_floats ? b.take<float>(s->wg_pool_floats) : nullptr;
 }
@@ -585,8 +587,10 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
              const upnerf_pass_io& io, PassBufs& p, Scratch& s) {
   const upnerf_net_config& cfg = a.cfg;
   const float* prm = io.params;
+  // d_params == NULL: the network is frozen (test-time optimisation, models/nerf_system_optmize.py:
+  // 253-266 trains only embedding_fine_a and se3_refine) -- every weight-gradient launch is skipped
   float* g = io.d_params;
-  UPNERF_REQUIRE(g, UPNERF_ERR_BAD_SHAPE, "render_bwd: d_params missing");
+  const bool wg = g != nullptr;
   const int64_t M = p.M, R = p.R;
   const int S = p.S;
   Packed& k = p.pk;
@@ -599,13 +603,17 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     const float* gf = io.g_feat;
     UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wsf, 1, W, s.gHFr, W, 1, R, W, L.F, nullptr, 0));
     UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bsf, nullptr, 0, s.gWs, c.st));
-    UPNERF_TRY(mm(c, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
-    UPNERF_TRY(colsum_any(gf, L.F, p.Wsum, R, L.F, g + L.bsf, c.st));
+    if (wg) {
+      UPNERF_TRY(mm(c, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(colsum_any(gf, L.F, p.Wsum, R, L.F, g + L.bsf, c.st));
+    }
     if (ph.cand) {
       UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wcf, 1, H, s.gG2r, H, 1, R, H, L.F, nullptr, 0));
       UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bcf, nullptr, 0, s.gWc, c.st));
-      UPNERF_TRY(mm(c, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
-      UPNERF_TRY(colsum_any(gf, L.F, p.Wcsum, R, L.F, g + L.bcf, c.st));
+      if (wg) {
+        UPNERF_TRY(mm(c, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
+        UPNERF_TRY(colsum_any(gf, L.F, p.Wcsum, R, L.F, g + L.bcf, c.st));
+      }
     }
   }
   const bool feat_grad = ph.feat;
@@ -635,61 +643,73 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // 3. rgb head, part 1: through the sigmoid / row-dots / ReLU -> dQ_pre (right half of [dG1p | dQp])
   if (ph.rgb) {
-    UPNERF_TRY(rgb_head_bwd(p.Q, H2, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H2, s.dBq, g + L.Wr2,
-                            g + L.br2, c.dtype, c.st));
+    UPNERF_TRY(rgb_head_bwd(p.Q, H2, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H2, s.dBq,
+                            wg ? g + L.Wr2 : s.gdump, wg ? g + L.br2 : s.gdump + 3 * H, c.dtype, c.st));
     // per-ray bias path: [PE(dir) | a_emb] columns of rgb_share_layer.0 and the appearance table
-    UPNERF_TRY(mm(c, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
+    if (wg)
+      UPNERF_TRY(mm(c, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
     if (L.ad > 0 && io.d_emb_a) {
       UPNERF_TRY(mm(c, s.dBq, H, 1, prm + L.Wr0 + front + L.in_dir, 1, L.rgb_in, s.dP, L.ad, 1, R, L.ad, H, nullptr, 0));
       UPNERF_TRY(scatter_add_rows(s.dP, L.ad, a.img_idx, R, L.ad, io.d_emb_a, c.st));
     }
-    UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dbq, 0, H * sizeof(float), c.st));
-    UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, s.dbq, nullptr, UPNERF_F32, c.st));
-    UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, c.st));
-    if (cfg.encode_feat) UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
+    if (wg) {
+      UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dbq, 0, H * sizeof(float), c.st));
+      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, s.dbq, nullptr, UPNERF_F32, c.st));
+      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, c.st));
+      if (cfg.encode_feat) UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
+    }
   }
 
   // 4. candidate head, part 1: candidate_sigma and candidate_encoding.2 -> dG1_pre (left half)
   if (ph.cand) {
     UPNERF_REQUIRE(dg2_from_feat, UPNERF_ERR_BAD_CONFIG, "candidate head without the feature path");
     // candidate_sigma: dw += sum dcsig g2, db += sum dcsig
-    UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, c.st));
     const Seg sgH{0, H, 0};
-    UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H2, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
+    if (wg) {
+      UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, c.st));
+      UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H2, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
+    }
     e = ep_none();
     e.aux = p.G1; e.ldaux = H2; e.aux_mode = 2;
     UPNERF_TRY(linear(c, s.dG2p, H, k.Wc2T, H, s.dG1p, H2, M, H, H, e));
     UPNERF_TRY(ray_sum128(s.dG1p, H2, R, S, s.dBc, c.dtype, c.st));
-    UPNERF_TRY(mm(c, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
-    UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, c.st));
+    if (wg) {
+      UPNERF_TRY(mm(c, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, c.st));
+    }
     if (io.d_emb_c) {
       UPNERF_TRY(mm(c, s.dBc, H, 1, prm + L.Wc0 + W, 1, W + L.cd, s.dCrows, L.cd, 1, R, L.cd, H, nullptr, 0));
       UPNERF_TRY(scatter_add_rows(s.dCrows, L.cd, a.img_idx, R, L.cd, io.d_emb_c, c.st));
     }
   }
 
+  // frozen weights and no pose gradient wanted: only the embedding tables needed a gradient and
+  // they have it -- the trunk backward is dead work
+  if (!wg && !a.d_rays) return UPNERF_OK;
+
   // 4b. the two head layers on HF: weight gradients and dHF (+)= [dG1p | dQp] [Wc1; Wq]
-  float* dWq_dst = cfg.encode_feat ? s.dWq : g + L.Wr0;
+  float* dWq_dst = cfg.encode_feat ? s.dWq : (wg ? g + L.Wr0 : nullptr);
   const int64_t ld_dWq = cfg.encode_feat ? W : L.rgb_in;
   const Seg sgW{0, W, 0};
   if (stack) {
     int src = 0, len = W, dst = 0;
-    UPNERF_TRY(wgrad_launch(s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, dWq_dst, ld_dWq, nullptr, M, H2, W, 1, &src,
-                            &len, &dst, c.wb, c.st));
+    if (wg)
+      UPNERF_TRY(wgrad_launch(s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, dWq_dst, ld_dWq, nullptr, M, H2, W, 1, &src,
+                              &len, &dst, c.wb, c.st));
     e = ep_none();
     if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
     UPNERF_TRY(linear(c, s.dG1p, H2, k.WcqT, H2, s.dHF, W, M, W, H2, e));
     dhf_live = true;
   } else {
     if (ph.rgb) {
-      UPNERF_TRY(wgrad(c, s.dQp, H2, p.HF, W, dWq_dst, ld_dWq, nullptr, M, H, W, &sgW, 1));
+      if (wg) UPNERF_TRY(wgrad(c, s.dQp, H2, p.HF, W, dWq_dst, ld_dWq, nullptr, M, H, W, &sgW, 1));
       e = ep_none();
       if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
       UPNERF_TRY(linear(c, s.dQp, H2, k.WqT, H2, s.dHF, W, M, W, H, e));
       dhf_live = true;
     }
     if (ph.cand) {
-      UPNERF_TRY(wgrad(c, s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, nullptr, M, H, W, &sgW, 1));
+      if (wg) UPNERF_TRY(wgrad(c, s.dG1p, H2, p.HF, W, g + L.Wc0, W + L.cd, nullptr, M, H, W, &sgW, 1));
       e = ep_none();
       if (dhf_live) { e.aux = s.dHF; e.ldaux = W; e.aux_mode = 1; }
       UPNERF_TRY(linear(c, s.dG1p, H2, k.Wc1T, H2, s.dHF, W, M, W, H, e));
@@ -698,9 +718,9 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   }
 
   // 5. xyz_encoding_final + share_sigma  ->  dH8_pre
-  UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, c.st));
+  if (wg) UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, c.st));
   UPNERF_REQUIRE(dhf_live, UPNERF_ERR_BAD_CONFIG, "backward without any gradient into xyz_encoding_final");
-  {
+  if (wg) {
     const Seg sgW{0, W, 0};
     UPNERF_TRY(wgrad(c, s.dHF, W, p.Hs[8], W, g + L.Wf, W, g + L.bf, M, W, W, &sgW, 1));
   }
@@ -732,7 +752,7 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     void* dnext = fused ? nullptr : s.dY[(8 - i) & 1];
     if (i == 4) {
       const Seg sg[2] = {{0, W, L.in_xyz}, {W, L.in_xyz, 0}};
-      UPNERF_TRY(wgrad(c, dcur, W, p.X4, X4W, g + L.Wl[4], W + L.in_xyz, g + L.bl[4], M, W, X4W, sg, 2));
+      if (wg) UPNERF_TRY(wgrad(c, dcur, W, p.X4, X4W, g + L.Wl[4], W + L.in_xyz, g + L.bl[4], M, W, X4W, sg, 2));
       if (!fused) {
         e = ep_none();
         e.aux = p.X4; e.ldaux = X4W; e.aux_mode = 2;
@@ -745,7 +765,7 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
       }
     } else if (i == 0) {
       const Seg sg{0, L.in_xyz, 0};
-      UPNERF_TRY(wgrad(c, dcur, W, PE, X4W, g + L.Wl[0], L.in_xyz, g + L.bl[0], M, W, PEW, &sg, 1));
+      if (wg) UPNERF_TRY(wgrad(c, dcur, W, PE, X4W, g + L.Wl[0], L.in_xyz, g + L.bl[0], M, W, PEW, &sg, 1));
       if (a.d_rays) {
         e = ep_none();
         if (dpe_live) { e.aux = s.dPE; e.ldaux = PEW; e.aux_mode = 1; }
@@ -753,7 +773,7 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
       }
     } else {
       const Seg sg{0, W, 0};
-      UPNERF_TRY(wgrad(c, dcur, W, p.Hs[i], W, g + L.Wl[i], W, g + L.bl[i], M, W, W, &sg, 1));
+      if (wg) UPNERF_TRY(wgrad(c, dcur, W, p.Hs[i], W, g + L.Wl[i], W, g + L.bl[i], M, W, W, &sg, 1));
       if (!fused) {
         e = ep_none();
         e.aux = p.Hs[i]; e.ldaux = W; e.aux_mode = 2;
@@ -773,7 +793,7 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // 9. rgb head, part 2 (needs dWq from the reduction): chain rule through the folded matrix
   //    Wq = W_rgb0[:, :F] W_sf
-  if (ph.rgb && cfg.encode_feat) {
+  if (wg && ph.rgb && cfg.encode_feat) {
     UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
     UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
     // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
@@ -866,8 +886,16 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
   wb.pool_floats = pl.scratch.wg_pool_floats;
   Ctx c{a->dtype, pl.es, as_stream(stream), wb.pool ? &wb : nullptr};
   const Phase ph = make_phase(a->cfg, a->sched_mult);
-  if (a->n_importance > 0) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch));
-  UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch));
+  // A pass none of whose outputs received a gradient contributes exact zeros everywhere (the fine
+  // depths come from DETACHED coarse weights, models/rendering.py:268-276): it is skipped.  That is
+  // the whole coarse pass of test-time optimisation, whose loss reads s_rgb_fine only
+  // (models/nerf_system_optmize.py:128).
+  auto live = [](const upnerf_pass_io& io) {
+    return io.g_c_weights || io.g_s_weights || io.g_c_depth || io.g_s_depth || io.g_t_weight || io.g_feat ||
+           io.g_s_rgb;
+  };
+  if (a->n_importance > 0 && live(a->fine)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch));
+  if (live(a->coarse)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch));
   return UPNERF_OK;
 }
 

@@ -156,12 +156,19 @@ class _RenderFn(torch.autograd.Function):
             grads[key] = torch.zeros_like(like)
             return grads[key]
 
+        # needs_input_grad order = forward's arguments: (meta, rays, flat_c, flat_f, emb_ca, emb_fa, emb_cc, emb_fc)
+        wants = {"coarse": need[2], "fine": need[3], "coarse_a": need[4], "fine_a": need[5], "coarse_c": need[6],
+                 "fine_c": need[7]}
         for which, flat, ea, ec in (("coarse", flat_c, emb_ca, emb_cc), ("fine", flat_f, emb_fa, emb_fc)):
             if flat is None:
                 continue
             io = getattr(a, which)
-            io.d_params = dest(which, flat).data_ptr()
-            io.d_emb_a, io.d_emb_c = L._vp(dest(which + "_a", ea)), L._vp(dest(which + "_c", ec))
+            # a frozen network (test-time optimisation): NULL d_params skips every weight-gradient launch
+            frozen = not wants[which] and sink.get(which) is None
+            io.d_params = None if frozen else dest(which, flat).data_ptr()
+            ga = None if (not wants[which + "_a"] and sink.get(which + "_a") is None) else dest(which + "_a", ea)
+            gc = None if (not wants[which + "_c"] and sink.get(which + "_c") is None) else dest(which + "_c", ec)
+            io.d_emb_a, io.d_emb_c = L._vp(ga), L._vp(gc)
         L.render_bwd(a)
         return (None, d_rays, grads.get("coarse"), grads.get("fine"), grads.get("coarse_a"),
                 grads.get("fine_a"), grads.get("coarse_c"), grads.get("fine_c"))

@@ -20,10 +20,13 @@ from . import _lib as L
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, flat: torch.nn.Parameter, segments, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, flat: torch.nn.Parameter, segments, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=0.0):
+        """`weight_decay` > 0 gives torch.optim.AdamW's decoupled decay (the reference's test-time
+        appearance optimiser, models/nerf_system_optmize.py:61: AdamW(lr=1e-1), default decay 1e-2)."""
         if not flat.is_cuda:
             raise L.UpnerfError("FlatAdam runs on CUDA buffers only (no CPU fallback)")
-        super().__init__([flat], dict(lr=lr, betas=betas, eps=eps))
+        super().__init__([flat], dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         merged = []
         for end, key in segments:           # merge neighbours of the same class
             if merged and merged[-1][1] == key:
@@ -69,5 +72,6 @@ class FlatAdam(torch.optim.Optimizer):
                 a.seg_step_size[i] = lr / (1.0 - b1 ** t)
                 a.seg_bc2_sqrt[i] = math.sqrt(1.0 - b2 ** t)
         a.beta1, a.beta2, a.eps = float(b1), float(b2), float(group["eps"])
+        a.decay_mul = 1.0 - lr * float(group.get("weight_decay", 0.0))
         L.adam_step(a)
         return None
