@@ -748,7 +748,10 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
 }
 
 extern "C" int64_t upnerf_trunk_mask_words(int64_t M) {
-  return upnerf::ceil_div64(M, upnerf::kTileM) * 8 * 8 * upnerf::kTileM;
+  // tiles are processed in CTA pairs: the pair's second CTA writes (all-zero) masks for a phantom
+  // tile when the tile count is odd, so the buffer covers an even number of tiles
+  const int64_t tiles = upnerf::ceil_div64(M, upnerf::kTileM);
+  return (tiles + (tiles & 1)) * 8 * 8 * upnerf::kTileM;
 }
 
 extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* stream) {

@@ -11,6 +11,7 @@
 // Per-ray inputs (appearance / candidate embeddings, direction encoding) enter their layers
 // as a per-ray bias, so nothing per-ray is ever repeated per sample.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -127,7 +128,8 @@ struct PassBufs {
 struct Scratch {
   void *dY[8], *dHF, *dG2p, *dG1p, *dQp, *dPE;  // dY[j] = gradient of layer (8-j)'s pre-activation
   float *dssig, *dcsig, *drgb;
-  float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows, *dWq, *dbq;
+  float *gHFr, *gG2r, *gWs, *gWc, *dBq, *dBc, *dP, *dCrows;
+  float *dWq2[2], *dbq2[2];  // per network pass (fine, coarse): read by side-stream work that outlives the pass
   float* gdump;              // sink of the tiny side-effect gradients when the weights are frozen
   float* wg_pool;            // split partials of the tcgen05 weight gradients (bf16 mode)
   uint64_t wg_pool_floats;
@@ -236,8 +238,10 @@ void carve_scratch(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, Scr
   s->dBc = b.take<float>(R * H);
   s->dP = b.take<float>(R * (L.in_dir + L.ad));
   s->dCrows = b.take<float>(R * (L.cd > 0 ? L.cd : 1));
-  s->dWq = b.take<float>(H * W);
-  s->dbq = b.take<float>(H);
+  for (int i = 0; i < 2; ++i) {
+    s->dWq2[i] = b.take<float>(H * W);
+    s->dbq2[i] = b.take<float>(H);
+  }
   s->gdump = b.take<float>(4 * H);
   s->wg_pool_floats = es == 2 ? wgrad_pool_floats() : 0;
   s->wg_pool = s->wg_pool_floats ? b.take<float>(s->wg_pool_floats) : nullptr;
@@ -292,7 +296,59 @@ struct Ctx {
   size_t es;
   cudaStream_t st;
   WgradBatch* wb;  // bf16 backward: weight gradients park split partials here (one reduce per pass)
+  // Leaf work (per-ray products, parameter-space chain rules, bias/embedding gradients: small,
+  // latency-bound launches nothing downstream in the pass waits for) goes to a second in-order stream
+  // so it runs beside the tensor-core chain instead of inside it.  side == st when disabled.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Ctx leaf() const { Ctx c = *this; c.st = side; c.wb = nullptr; return c; }
+  bool has_side() const { return side != st; }
 };
+
+// One side stream and one fork/join event pair per device, created on first use and kept for the
+// life of the process (UPNERF_SIDE_STREAM=0 disables the overlap: everything stays on one stream).
+struct SideRes { cudaStream_t st; cudaEvent_t fork_ev, join_ev; int state; };
+SideRes* side_res() {
+  static SideRes res[32];
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("UPNERF_SIDE_STREAM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  SideRes& r = res[dev];
+  if (r.state == 0) {
+    r.state = -1;
+    if (cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&r.fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&r.join_ev, cudaEventDisableTiming) == cudaSuccess)
+      r.state = 1;
+  }
+  return r.state == 1 ? &r : nullptr;
+}
+Ctx make_ctx(int dtype, size_t es, cudaStream_t st, WgradBatch* wb) {
+  Ctx c;
+  c.dtype = dtype; c.es = es; c.st = st; c.wb = wb;
+  c.side = st;
+  if (SideRes* r = side_res()) { c.side = r->st; c.ev_fork = r->fork_ev; c.ev_join = r->join_ev; }
+  return c;
+}
+// side stream picks up everything launched on the main stream so far
+int fork_side(const Ctx& c) {
+  if (!c.has_side()) return UPNERF_OK;
+  UPNERF_CHECK_CUDA(cudaEventRecord(c.ev_fork, c.st));
+  UPNERF_CHECK_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+  return UPNERF_OK;
+}
+// main stream waits for everything launched on the side stream so far
+int join_side(const Ctx& c) {
+  if (!c.has_side()) return UPNERF_OK;
+  UPNERF_CHECK_CUDA(cudaEventRecord(c.ev_join, c.side));
+  UPNERF_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.ev_join, 0));
+  return UPNERF_OK;
+}
 
 inline void* col(void* p, int64_t c, size_t es) { return static_cast<uint8_t*>(p) + c * es; }
 inline const void* col(const void* p, int64_t c, size_t es) { return static_cast<const uint8_t*>(p) + c * es; }
@@ -362,7 +418,10 @@ upnerf_epilogue ep_none() {
 }
 
 // ------------------------------------------------------------------ weight packing
-int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L, const Phase& ph,
+// The trunk operands are packed on the main stream (the fused trunk needs them first); the head
+// operands -- behind the folded-matrix product Wq = W_rgb0[:, :F] W_sf -- on the side stream `cl`,
+// which the caller joins before the first head layer.
+int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, const NetLayout& L, const Phase& ph,
                  const float* prm, Packed& k) {
   UPNERF_CHECK_CUDA(cudaMemsetAsync(k.region, 0, k.region_bytes, c.st));
   UPNERF_TRY(upnerf_c2f_weights(prm + L.progress, cfg.c2f_start, cfg.c2f_end, cfg.use_c2f, cfg.xyz_L,
@@ -390,6 +449,9 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
   add(prm + L.Wl[4], W + ix, k.W5peT, W, W, ix, 1);
   add(prm + L.Wf, W, k.WF, WCAT, W, W, 0);
   add(prm + L.Wf, W, k.WFT, WCATT, W, W, 1);
+  UPNERF_TRY(run_pack(pl, c.dtype, c.st));
+  UPNERF_TRY(fork_side(c));
+  pl.n = 0;
   if (ph.cand) {
     add(prm + L.Wc0, W + L.cd, k.Wc1, W, H, W, 0);
     add(prm + L.Wc0, W + L.cd, k.Wc1T, 2 * H, H, W, 1);
@@ -399,20 +461,20 @@ int pack_weights(const Ctx& c, const upnerf_net_config& cfg, const NetLayout& L,
   if (ph.rgb) {
     if (cfg.encode_feat) {
       // Wq = W_rgb0[:, :F] W_sf  (128 x 256);  bq_const = W_rgb0[:, :F] b_sf + b_rgb0
-      UPNERF_TRY(mm(c, prm + L.Wr0, L.rgb_in, 1, prm + L.Wsf, 1, W, k.Wq32, W, 1, H, W, L.F, nullptr, 0));
+      UPNERF_TRY(mm(cl, prm + L.Wr0, L.rgb_in, 1, prm + L.Wsf, 1, W, k.Wq32, W, 1, H, W, L.F, nullptr, 0));
       upnerf_epilogue e = ep_none();
       e.bias = prm + L.br0;
-      UPNERF_TRY(mm(c, prm + L.bsf, 0, 1, prm + L.Wr0, L.rgb_in, 1, k.bq_const, 0, 1, 1, H, L.F, &e, 0));
+      UPNERF_TRY(mm(cl, prm + L.bsf, 0, 1, prm + L.Wr0, L.rgb_in, 1, k.bq_const, 0, 1, 1, H, L.F, &e, 0));
       add(k.Wq32, W, k.Wq, W, H, W, 0);
       add(k.Wq32, W, k.WqT, 2 * H, H, W, 1);
     } else {
       UPNERF_CHECK_CUDA(cudaMemcpyAsync(k.bq_const, prm + L.br0, H * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, c.st));
+                                        cudaMemcpyDeviceToDevice, cl.st));
       add(prm + L.Wr0, L.rgb_in, k.Wq, W, H, W, 0);
       add(prm + L.Wr0, L.rgb_in, k.WqT, 2 * H, H, W, 1);
     }
   }
-  return run_pack(pl, c.dtype, c.st);
+  return pl.n ? run_pack(pl, c.dtype, cl.st) : UPNERF_OK;
 }
 
 // ------------------------------------------------------------------ one network, forward
@@ -423,14 +485,50 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   const int64_t M = p.M, R = p.R;
   const int S = p.S;
   Packed& k = p.pk;
-  UPNERF_TRY(pack_weights(c, cfg, L, ph, prm, k));
+  const Ctx cl = c.leaf();
+  UPNERF_TRY(pack_weights(c, cl, cfg, L, ph, prm, k));   // forks the side stream
+
+  // Per-ray inputs of the head layers (embeddings, direction encoding) enter as a per-ray bias
+  // W[:, cols] e_ray: computed on the side stream while the trunk runs.
+  const int H2 = 2 * H;
+  const bool stack = ph.cand && ph.rgb && c.dtype == UPNERF_BF16;
+  float* Bc = p.Bc;
+  float* Bq = stack ? p.Bc + H : p.Bq;
+  const int64_t ldbias = stack ? H2 : H;
+  upnerf_epilogue e = ep_none();
+  if (ph.cand) {
+    // per-ray bias of candidate_encoding.0: W[:, 256:] c_emb + b
+    UPNERF_TRY(gather_rows(io.emb_c, a.img_idx, R, L.cd, p.Crows, L.cd, cl.st));
+    e = ep_none();
+    e.bias = prm + L.bc0;
+    UPNERF_TRY(mm(cl, p.Crows, L.cd, 1, prm + L.Wc0 + W, W + L.cd, 1, Bc, ldbias, 1, R, H, L.cd, &e, 0));
+  }
+  if (ph.rgb) {
+    // per-ray bias of rgb_share_layer.0: W[:, F:] [PE(dir) | a_emb] + (W[:, :F] b_sf + b)
+    const int pw = L.in_dir + L.ad;
+    UPNERF_TRY(upnerf_posenc_fwd(a.rays + 3, 8, R, cfg.dir_L, k.band_dir, p.P, pw, L.in_dir, UPNERF_F32, cl.st));
+    if (L.ad > 0) {
+      if (cfg.encode_appearance) UPNERF_TRY(gather_rows(io.emb_a, a.img_idx, R, L.ad, p.P + L.in_dir, pw, cl.st));
+      else UPNERF_REQUIRE(false, UPNERF_ERR_BAD_CONFIG, "appearance_dim > 0 with encode_appearance off");
+    }
+    const int front = cfg.encode_feat ? L.F : W;
+    e = ep_none();
+    e.bias = k.bq_const;
+    UPNERF_TRY(mm(cl, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, Bq, ldbias, 1, R, H, pw, &e, 0));
+  }
+  if (stack) {
+    // rgb_share_layer.2 row-dots see only the Q half of the stacked output
+    UPNERF_CHECK_CUDA(cudaMemsetAsync(k.hw3, 0, 3 * H2 * sizeof(float), cl.st));
+    UPNERF_CHECK_CUDA(cudaMemcpy2DAsync(k.hw3 + H, H2 * sizeof(float), prm + L.Wr2, H * sizeof(float),
+                                        H * sizeof(float), 3, cudaMemcpyDeviceToDevice, cl.st));
+  }
 
   // positional encoding of x = o + d z straight into the skip buffer [H4 | PE]
   void* PE = col(p.X4, W, c.es);
   UPNERF_TRY(upnerf_points_posenc_fwd(a.rays, p.z, R, S, cfg.xyz_L, k.band_xyz, PE, X4W, PEW, c.dtype, c.st));
 
   // trunk + xyz_encoding_final (+ share_sigma on layer 8)
-  upnerf_epilogue e = ep_none();
+  e = ep_none();
   if (c.dtype == UPNERF_BF16) {
     // one persistent tcgen05 kernel; activations stay in shared memory between layers
     upnerf_trunk_args ta;
@@ -479,37 +577,9 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // Head layers on HF.  candidate_encoding.0 and (folded) rgb_share_layer.0 read the same input, so
   // with both live (phase 1) they run as ONE stacked 256-wide GEMM into the side-by-side buffer
-  // [G1 | Q]; per-ray inputs (embeddings, direction encoding) enter as a per-ray bias.
-  const int H2 = 2 * H;
-  const bool stack = ph.cand && ph.rgb && c.dtype == UPNERF_BF16;
-  float* Bc = p.Bc;
-  float* Bq = stack ? p.Bc + H : p.Bq;
-  const int64_t ldbias = stack ? H2 : H;
-  if (ph.cand) {
-    // per-ray bias of candidate_encoding.0: W[:, 256:] c_emb + b
-    UPNERF_TRY(gather_rows(io.emb_c, a.img_idx, R, L.cd, p.Crows, L.cd, c.st));
-    e = ep_none();
-    e.bias = prm + L.bc0;
-    UPNERF_TRY(mm(c, p.Crows, L.cd, 1, prm + L.Wc0 + W, W + L.cd, 1, Bc, ldbias, 1, R, H, L.cd, &e, 0));
-  }
-  if (ph.rgb) {
-    // per-ray bias of rgb_share_layer.0: W[:, F:] [PE(dir) | a_emb] + (W[:, :F] b_sf + b)
-    const int pw = L.in_dir + L.ad;
-    UPNERF_TRY(upnerf_posenc_fwd(a.rays + 3, 8, R, cfg.dir_L, k.band_dir, p.P, pw, L.in_dir, UPNERF_F32, c.st));
-    if (L.ad > 0) {
-      if (cfg.encode_appearance) UPNERF_TRY(gather_rows(io.emb_a, a.img_idx, R, L.ad, p.P + L.in_dir, pw, c.st));
-      else UPNERF_REQUIRE(false, UPNERF_ERR_BAD_CONFIG, "appearance_dim > 0 with encode_appearance off");
-    }
-    const int front = cfg.encode_feat ? L.F : W;
-    e = ep_none();
-    e.bias = k.bq_const;
-    UPNERF_TRY(mm(c, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, Bq, ldbias, 1, R, H, pw, &e, 0));
-  }
+  // [G1 | Q]; the per-ray biases and head operands come from the side stream.
+  UPNERF_TRY(join_side(c));
   if (stack) {
-    // rgb_share_layer.2 row-dots see only the Q half of the stacked output
-    UPNERF_CHECK_CUDA(cudaMemsetAsync(k.hw3, 0, 3 * H2 * sizeof(float), c.st));
-    UPNERF_CHECK_CUDA(cudaMemcpy2DAsync(k.hw3 + H, H2 * sizeof(float), prm + L.Wr2, H * sizeof(float),
-                                        H * sizeof(float), 3, cudaMemcpyDeviceToDevice, c.st));
     e = ep_none();
     e.act = 1;
     e.ray_bias = Bc;
@@ -568,15 +638,17 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   if (ph.feat) {
     // feat = W_sf (sum w hF) + b_sf sum w  [+ W_cf (sum w' g2) + b_cf sum w']
     UPNERF_REQUIRE(io.feat, UPNERF_ERR_BAD_SHAPE, "feat output missing");
+    // (side stream: the caller joins once per render, so the coarse projections overlap the fine pass)
+    UPNERF_TRY(fork_side(c));
     e = ep_none();
     e.rank1_row = p.Wsum;
     e.rank1_col = prm + L.bsf;
-    UPNERF_TRY(mm(c, p.HFr, W, 1, prm + L.Wsf, W, 1, io.feat, L.F, 1, R, L.F, W, &e, 0));
+    UPNERF_TRY(mm(cl, p.HFr, W, 1, prm + L.Wsf, W, 1, io.feat, L.F, 1, R, L.F, W, &e, 0));
     if (ph.cand) {
       e = ep_none();
       e.rank1_row = p.Wcsum;
       e.rank1_col = prm + L.bcf;
-      UPNERF_TRY(mm(c, p.G2r, H, 1, prm + L.Wcf, H, 1, io.feat, L.F, 1, R, L.F, H, &e, 1));
+      UPNERF_TRY(mm(cl, p.G2r, H, 1, prm + L.Wcf, H, 1, io.feat, L.F, 1, R, L.F, H, &e, 1));
     }
   }
   return UPNERF_OK;
@@ -584,13 +656,15 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
 // ------------------------------------------------------------------ one network, backward
 int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
-             const upnerf_pass_io& io, PassBufs& p, Scratch& s) {
+             const upnerf_pass_io& io, PassBufs& p, Scratch& s, int which) {
   const upnerf_net_config& cfg = a.cfg;
   const float* prm = io.params;
   // d_params == NULL: the network is frozen (test-time optimisation, models/nerf_system_optmize.py:
   // 253-266 trains only embedding_fine_a and se3_refine) -- every weight-gradient launch is skipped
   float* g = io.d_params;
   const bool wg = g != nullptr;
+  float* const dWq = s.dWq2[which];
+  float* const dbq = s.dbq2[which];
   const int64_t M = p.M, R = p.R;
   const int S = p.S;
   Packed& k = p.pk;
@@ -599,21 +673,25 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   // 1. per-ray feature projections
   UPNERF_REQUIRE(!ph.feat || io.g_feat, UPNERF_ERR_BAD_SHAPE,
                  "render_bwd: g_feat is required in this phase (pass zeros when unused)");
+  // Weight-gradient leaves (nothing later in the pass reads them) go to the side stream `cl`; the
+  // main stream joins it once, before the split reduction at the end of the pass.
+  const Ctx cl = c.leaf();
+  UPNERF_TRY(fork_side(c));
   if (ph.feat) {
     const float* gf = io.g_feat;
+    if (wg) {
+      UPNERF_TRY(mm(cl, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(colsum_any(gf, L.F, p.Wsum, R, L.F, g + L.bsf, cl.st));
+      if (ph.cand) {
+        UPNERF_TRY(mm(cl, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
+        UPNERF_TRY(colsum_any(gf, L.F, p.Wcsum, R, L.F, g + L.bcf, cl.st));
+      }
+    }
     UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wsf, 1, W, s.gHFr, W, 1, R, W, L.F, nullptr, 0));
     UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bsf, nullptr, 0, s.gWs, c.st));
-    if (wg) {
-      UPNERF_TRY(mm(c, gf, 1, L.F, p.HFr, 1, W, g + L.Wsf, W, 1, L.F, W, R, nullptr, 0, split_for(R)));
-      UPNERF_TRY(colsum_any(gf, L.F, p.Wsum, R, L.F, g + L.bsf, c.st));
-    }
     if (ph.cand) {
       UPNERF_TRY(mm(c, gf, L.F, 1, prm + L.Wcf, 1, H, s.gG2r, H, 1, R, H, L.F, nullptr, 0));
       UPNERF_TRY(rowdot_head(gf, L.F, R, L.F, 1, prm + L.bcf, nullptr, 0, s.gWc, c.st));
-      if (wg) {
-        UPNERF_TRY(mm(c, gf, 1, L.F, p.G2r, 1, H, g + L.Wcf, H, 1, L.F, H, R, nullptr, 0, split_for(R)));
-        UPNERF_TRY(colsum_any(gf, L.F, p.Wcsum, R, L.F, g + L.bcf, c.st));
-      }
     }
   }
   const bool feat_grad = ph.feat;
@@ -646,17 +724,18 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     UPNERF_TRY(rgb_head_bwd(p.Q, H2, p.rgb, s.drgb, prm + L.Wr2, R, S, s.dQp, H2, s.dBq,
                             wg ? g + L.Wr2 : s.gdump, wg ? g + L.br2 : s.gdump + 3 * H, c.dtype, c.st));
     // per-ray bias path: [PE(dir) | a_emb] columns of rgb_share_layer.0 and the appearance table
+    UPNERF_TRY(fork_side(c));
     if (wg)
-      UPNERF_TRY(mm(c, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(mm(cl, s.dBq, 1, H, p.P, 1, pw, g + L.Wr0 + front, L.rgb_in, 1, H, pw, R, nullptr, 0, split_for(R)));
     if (L.ad > 0 && io.d_emb_a) {
-      UPNERF_TRY(mm(c, s.dBq, H, 1, prm + L.Wr0 + front + L.in_dir, 1, L.rgb_in, s.dP, L.ad, 1, R, L.ad, H, nullptr, 0));
-      UPNERF_TRY(scatter_add_rows(s.dP, L.ad, a.img_idx, R, L.ad, io.d_emb_a, c.st));
+      UPNERF_TRY(mm(cl, s.dBq, H, 1, prm + L.Wr0 + front + L.in_dir, 1, L.rgb_in, s.dP, L.ad, 1, R, L.ad, H, nullptr, 0));
+      UPNERF_TRY(scatter_add_rows(s.dP, L.ad, a.img_idx, R, L.ad, io.d_emb_a, cl.st));
     }
     if (wg) {
-      UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dbq, 0, H * sizeof(float), c.st));
-      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, s.dbq, nullptr, UPNERF_F32, c.st));
-      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, c.st));
-      if (cfg.encode_feat) UPNERF_CHECK_CUDA(cudaMemsetAsync(s.dWq, 0, H * W * sizeof(float), c.st));
+      UPNERF_CHECK_CUDA(cudaMemsetAsync(dbq, 0, H * sizeof(float), cl.st));
+      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, dbq, nullptr, UPNERF_F32, cl.st));
+      UPNERF_TRY(rowscale_colsum(s.dBq, H, nullptr, R, H, g + L.br0, nullptr, UPNERF_F32, cl.st));
+      if (cfg.encode_feat) UPNERF_CHECK_CUDA(cudaMemsetAsync(dWq, 0, H * W * sizeof(float), c.st));
     }
   }
 
@@ -666,29 +745,31 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     // candidate_sigma: dw += sum dcsig g2, db += sum dcsig
     const Seg sgH{0, H, 0};
     if (wg) {
-      UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, c.st));
+      UPNERF_TRY(fork_side(c));
+      UPNERF_TRY(rowscale_colsum(p.G2, H, s.dcsig, M, H, g + L.Wcs, g + L.bcs, c.dtype, cl.st));
       UPNERF_TRY(wgrad(c, s.dG2p, H, p.G1, H2, g + L.Wc2, H, g + L.bc2, M, H, H, &sgH, 1));
     }
     e = ep_none();
     e.aux = p.G1; e.ldaux = H2; e.aux_mode = 2;
     UPNERF_TRY(linear(c, s.dG2p, H, k.Wc2T, H, s.dG1p, H2, M, H, H, e));
     UPNERF_TRY(ray_sum128(s.dG1p, H2, R, S, s.dBc, c.dtype, c.st));
+    UPNERF_TRY(fork_side(c));
     if (wg) {
-      UPNERF_TRY(mm(c, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
-      UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, c.st));
+      UPNERF_TRY(mm(cl, s.dBc, 1, H, p.Crows, 1, L.cd, g + L.Wc0 + W, W + L.cd, 1, H, L.cd, R, nullptr, 0, split_for(R)));
+      UPNERF_TRY(rowscale_colsum(s.dBc, H, nullptr, R, H, g + L.bc0, nullptr, UPNERF_F32, cl.st));
     }
     if (io.d_emb_c) {
-      UPNERF_TRY(mm(c, s.dBc, H, 1, prm + L.Wc0 + W, 1, W + L.cd, s.dCrows, L.cd, 1, R, L.cd, H, nullptr, 0));
-      UPNERF_TRY(scatter_add_rows(s.dCrows, L.cd, a.img_idx, R, L.cd, io.d_emb_c, c.st));
+      UPNERF_TRY(mm(cl, s.dBc, H, 1, prm + L.Wc0 + W, 1, W + L.cd, s.dCrows, L.cd, 1, R, L.cd, H, nullptr, 0));
+      UPNERF_TRY(scatter_add_rows(s.dCrows, L.cd, a.img_idx, R, L.cd, io.d_emb_c, cl.st));
     }
   }
 
   // frozen weights and no pose gradient wanted: only the embedding tables needed a gradient and
   // they have it -- the trunk backward is dead work
-  if (!wg && !a.d_rays) return UPNERF_OK;
+  if (!wg && !a.d_rays) return join_side(c);
 
   // 4b. the two head layers on HF: weight gradients and dHF (+)= [dG1p | dQp] [Wc1; Wq]
-  float* dWq_dst = cfg.encode_feat ? s.dWq : (wg ? g + L.Wr0 : nullptr);
+  float* dWq_dst = cfg.encode_feat ? dWq : (wg ? g + L.Wr0 : nullptr);
   const int64_t ld_dWq = cfg.encode_feat ? W : L.rgb_in;
   const Seg sgW{0, W, 0};
   if (stack) {
@@ -718,7 +799,10 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
   }
 
   // 5. xyz_encoding_final + share_sigma  ->  dH8_pre
-  if (wg) UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, c.st));
+  if (wg) {
+    UPNERF_TRY(fork_side(c));
+    UPNERF_TRY(rowscale_colsum(p.Hs[8], W, s.dssig, M, W, g + L.Ws, g + L.bs, c.dtype, cl.st));
+  }
   UPNERF_REQUIRE(dhf_live, UPNERF_ERR_BAD_CONFIG, "backward without any gradient into xyz_encoding_final");
   if (wg) {
     const Seg sgW{0, W, 0};
@@ -789,16 +873,19 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // 8. every tcgen05 weight gradient of this pass has parked its split partials: one reduction
   //    launch sums them (fixed order) into the parameter gradients
+  UPNERF_TRY(join_side(c));
   if (c.wb) UPNERF_TRY(wgrad_reduce(c.wb, c.st));
 
   // 9. rgb head, part 2 (needs dWq from the reduction): chain rule through the folded matrix
   //    Wq = W_rgb0[:, :F] W_sf
+  //    (side stream again; it trails into the next pass and is joined at the end of the render backward)
   if (wg && ph.rgb && cfg.encode_feat) {
-    UPNERF_TRY(mm(c, s.dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
-    UPNERF_TRY(mm(c, prm + L.Wr0, 1, L.rgb_in, s.dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
+    UPNERF_TRY(fork_side(c));
+    UPNERF_TRY(mm(cl, dWq, W, 1, prm + L.Wsf, W, 1, g + L.Wr0, L.rgb_in, 1, H, L.F, W, nullptr, 1));
+    UPNERF_TRY(mm(cl, prm + L.Wr0, 1, L.rgb_in, dWq, 1, W, g + L.Wsf, W, 1, L.F, W, H, nullptr, 1));
     // bq_const = W_rgb0[:, :F] b_sf + b_rgb0
-    UPNERF_TRY(mm(c, s.dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
-    UPNERF_TRY(mm(c, s.dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
+    UPNERF_TRY(mm(cl, dbq, 0, 1, prm + L.Wr0, 1, L.rgb_in, g + L.bsf, 0, 1, 1, L.F, H, nullptr, 1));
+    UPNERF_TRY(mm(cl, dbq, 1, 0, prm + L.bsf, 1, 0, g + L.Wr0, L.rgb_in, 1, H, L.F, 1, nullptr, 1));
   }
   return UPNERF_OK;
 }
@@ -837,7 +924,7 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   UPNERF_REQUIRE(a->workspace_bytes >= pl.bytes, UPNERF_ERR_WORKSPACE,
                  "workspace too small: %llu < %llu bytes", (unsigned long long)a->workspace_bytes,
                  (unsigned long long)pl.bytes);
-  Ctx c{a->dtype, pl.es, as_stream(stream), nullptr};
+  const Ctx c = make_ctx(a->dtype, pl.es, as_stream(stream), nullptr);
   const Phase ph = make_phase(a->cfg, a->sched_mult);
   const int64_t R = a->n_rays;
   const int S = a->n_samples;
@@ -846,7 +933,7 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   if (a->z_coarse)
     UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_coarse, pl.coarse.z, R * S * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
   UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->coarse, pl.coarse));
-  if (a->n_importance == 0) return UPNERF_OK;
+  if (a->n_importance == 0) return join_side(c);
 
   // hierarchical resampling (models/rendering.py:262-307)
   const float* w0 = nullptr;
@@ -870,7 +957,7 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   if (a->z_fine)
     UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_fine, pl.fine.z, R * pl.S_f * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
   UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->fine, pl.fine));
-  return UPNERF_OK;
+  return join_side(c);
 }
 
 int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
@@ -884,7 +971,7 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
   memset(&wb, 0, sizeof(wb));
   wb.pool = pl.scratch.wg_pool;
   wb.pool_floats = pl.scratch.wg_pool_floats;
-  Ctx c{a->dtype, pl.es, as_stream(stream), wb.pool ? &wb : nullptr};
+  const Ctx c = make_ctx(a->dtype, pl.es, as_stream(stream), wb.pool ? &wb : nullptr);
   const Phase ph = make_phase(a->cfg, a->sched_mult);
   // A pass none of whose outputs received a gradient contributes exact zeros everywhere (the fine
   // depths come from DETACHED coarse weights, models/rendering.py:268-276): it is skipped.  That is
@@ -894,9 +981,9 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
     return io.g_c_weights || io.g_s_weights || io.g_c_depth || io.g_s_depth || io.g_t_weight || io.g_feat ||
            io.g_s_rgb;
   };
-  if (a->n_importance > 0 && live(a->fine)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch));
-  if (live(a->coarse)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch));
-  return UPNERF_OK;
+  if (a->n_importance > 0 && live(a->fine)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch, 0));
+  if (live(a->coarse)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch, 1));
+  return join_side(c);
 }
 
 }  // extern "C"

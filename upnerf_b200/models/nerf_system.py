@@ -16,6 +16,7 @@ deliberate and invisible to results:
 from __future__ import annotations
 
 import math
+import os
 from collections import defaultdict
 
 import torch
@@ -49,6 +50,8 @@ def default_hparams() -> dict:
         "pose.optimize": True, "pose.c2f": (0.1, 0.5), "pose.noise": -1,
         "candidate_schedule": (0.1, 0.5),
         "kernel.precision": "bf16",
+        # TransientNet on a second CUDA stream beside the render (UPNERF_TNET_SIDE=0 turns it off)
+        "kernel.side_stream": os.environ.get("UPNERF_TNET_SIDE", "1") != "0",
         "kernel.fused_tail": True,      # depth correction + loss + its backward + psnr as one launch (CUDA only)
     }
 
@@ -140,6 +143,7 @@ class NeRFSystem(nn.Module):
         self._device = torch.device(device)
         self._progress = 0.0
         self._tail_ws = None
+        self._side_stream = None
         self.white_back = False
         if N_images_train is not None:
             self.model_setup(N_images_train)
@@ -276,6 +280,19 @@ class NeRFSystem(nn.Module):
         hp = self.hparams
         B = rays.shape[0]
         chunk = B if train else hp["val.chunk_size"]
+        # TransientNet reads only (feats, img_idx): on the CUDA path it runs on a second stream beside the
+        # render (autograd runs its backward on that stream too, beside the render backward)
+        t, side = None, None
+        if sched_mult > 0 and rays.is_cuda and hp["kernel.side_stream"]:
+            main = torch.cuda.current_stream(rays.device)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=rays.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                t = self.transient_net(feats, img_idx)
+            feats.record_stream(side)
+            img_idx.record_stream(side)
         results = defaultdict(list)
         for i in range(0, B, chunk):
             part = render_rays(models=self.models, embeddings=self.embeddings, rays=rays[i:i + chunk],
@@ -290,7 +307,12 @@ class NeRFSystem(nn.Module):
                 results[k].append(v)
         results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
         if sched_mult > 0:
-            t = self.transient_net(feats, img_idx)
+            if t is None:
+                t = self.transient_net(feats, img_idx)
+            else:
+                main.wait_stream(side)
+                for v in t.values():
+                    v.record_stream(main)
             a, c = t["alpha"], t["rgb"]
             if blend:
                 results["rgb_coarse"] = results["s_rgb_coarse"] * (1 - a.detach()) + c.detach() * a.detach()
