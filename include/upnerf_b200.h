@@ -442,6 +442,48 @@ typedef struct upnerf_adam_args {
 } upnerf_adam_args;
 int upnerf_adam_step(const upnerf_adam_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (f1) GPU-resident training-ray batcher.
+ * Replaces PhototourismDataset.__getitem__ (split "train", datasets/phototourism.py:420-454)
+ * applied to every index of a batch plus torch's default_collate, i.e. what the reference's
+ * DataLoader workers do per RAY in Python (2048+ calls per step) followed by the H2D copy.
+ * The per-ray tables the reference builds once (datasets/phototourism.py:213-323: all_ray_infos,
+ * all_directions, all_rgbs, all_pxl_coords, all_inv_depths, feat_maps) and the per-image start
+ * poses (poses_dict, :181-211) stay resident in HBM; one launch gathers a batch:
+ *   img_idx   = (int64) ray_infos[idx, 2]                       (:422)
+ *   ray_infos = ray_infos[idx, :2], directions, rgbs, inv_depths = table[idx]   (:423-428, :451)
+ *   c2w       = poses[img_idx]                                  (:427)
+ *   feats     = the reference's 4-tap interpolation of feat_maps[img_idx] at
+ *               pxl_coords[idx] * (h - 1)  (:430-450), INCLUDING its border behaviour: with
+ *               y2 = min(h-1, y1+1) a sample exactly on the last row/column gets all-zero weights.
+ *               Products and sums are separately rounded fp32 in the reference's order
+ *               ((w11 p11 + w12 p12) + w21 p21) + w22 p22 -- results are bit-identical.
+ * status (optional, device int32): bit 0 is set when an index or image id is out of range (the
+ * reference raises IndexError; such rays are skipped here).  HBM-bound gather: 4*F*4 bytes read and
+ * F*4 written per ray for the features + ~200 B of small fields (7.9 KB/ray at F = 384). */
+typedef struct upnerf_ray_batch_args {
+  int64_t n_rays;              /* R: batch size */
+  int64_t n_total;             /* N: rows of the per-ray tables */
+  int n_images, feat_h, feat_w, feat_dim;   /* the reference asserts feat_h == feat_w (:431) */
+  const int64_t* idx;          /* [R] ray indices into the tables */
+  const float* ray_infos;      /* [N,3] = (near, far, image index as float) */
+  const float* directions;     /* [N,3] */
+  const float* rgbs;           /* [N,3] */
+  const float* pxl_coords;     /* [N,2] = (y, x) in [0,1]; NULL with feat_maps NULL */
+  const float* inv_depths;     /* [N] or NULL */
+  const float* feat_maps;      /* [n_images, feat_h, feat_w, feat_dim] or NULL */
+  const float* poses;          /* [n_images,3,4] */
+  float* out_ray_infos;        /* [R,2] */
+  float* out_directions;       /* [R,3] */
+  int64_t* out_img_idx;        /* [R] */
+  float* out_c2w;              /* [R,3,4] */
+  float* out_rgbs;             /* [R,3] */
+  float* out_feats;            /* [R,feat_dim] or NULL */
+  float* out_inv_depths;       /* [R] or NULL */
+  int* status;                 /* optional */
+} upnerf_ray_batch_args;
+int upnerf_ray_batch_gather(const upnerf_ray_batch_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -315,6 +315,37 @@ def gen_tail(ref_tnet, ref_losses):
     _save("tail", **arrays)
 
 
+def gen_ray_batch():
+    """`PhototourismDataset.__getitem__` (split "train", datasets/phototourism.py:420-454) + default_collate on
+    synthetic tables.  The constructor reads a COLMAP scene from disk, so the object is made with
+    `object.__new__` and given exactly the attributes `__getitem__` reads; the method itself is the
+    reference's, unmodified."""
+    from torch.utils.data import default_collate
+
+    import datasets.phototourism as ref_ds
+
+    from . import ray_batch as RB
+
+    n_img, img_h, img_w, fh, C = 3, 7, 9, 5, 12
+    t = RB.synth_tables(n_img, img_h, img_w, fh, C, seed=11)
+    ds = object.__new__(ref_ds.PhototourismDataset)
+    ds.split, ds.feat_map_dir = "train", "synthetic"
+    ds.all_ray_infos, ds.all_directions, ds.all_rgbs = t["all_ray_infos"], t["all_directions"], t["all_rgbs"]
+    ds.all_pxl_coords, ds.all_inv_depths, ds.feat_maps = t["all_pxl_coords"], t["all_inv_depths"], t["feat_maps"]
+    ds.img_ids_train = [100 + 7 * i for i in range(n_img)]
+    ds.poses_dict = {id_: t["poses"][i].numpy() for i, id_ in enumerate(ds.img_ids_train)}
+    N = t["all_ray_infos"].shape[0]
+    g = torch.Generator().manual_seed(5)
+    # every ray of image 1 (all border cases: last row, last column, corner) + a shuffled sample
+    idx = torch.cat([torch.arange(img_h * img_w, 2 * img_h * img_w), torch.randperm(N, generator=g)[:64]])
+    batch = default_collate([ds[int(i)] for i in idx])
+    arrays = {f"tab__{k}": v for k, v in t.items()}
+    arrays["idx"] = idx
+    for k, v in batch.items():
+        arrays[f"out__{k}"] = v
+    _save("ray_batch", **arrays)
+
+
 def main():
     ref_nerf, ref_rendering, ref_camera, ref_ray, ref_tnet, ref_losses = _import_reference()
     torch.set_num_threads(4)
@@ -325,6 +356,7 @@ def main():
     gen_nerf_forward(ref_nerf)
     gen_render_rays(ref_nerf, ref_rendering)
     gen_tail(ref_tnet, ref_losses)
+    gen_ray_batch()
 
 
 if __name__ == "__main__":

@@ -31,13 +31,15 @@ def test_struct_layouts_match_header(libpath, tmp_path):
     from upnerf_b200 import _lib as L
 
     src = tmp_path / "sz.cpp"
-    src.write_text('#include "upnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include "upnerf_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(upnerf_render_args),sizeof(upnerf_composite_args),sizeof(upnerf_net_config),"
-                   "sizeof(upnerf_pass_io),sizeof(upnerf_epilogue));}\n")
+                   "sizeof(upnerf_pass_io),sizeof(upnerf_epilogue),sizeof(upnerf_ray_batch_args),"
+                   "sizeof(upnerf_tail_args),sizeof(upnerf_adam_args));}\n")
     exe = tmp_path / "sz"
     subprocess.run(["g++", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [ctypes.sizeof(t) for t in (L.RenderArgs, L.CompositeArgs, L.NetConfig, L.PassIO, L.Epilogue)]
+    want = [ctypes.sizeof(t) for t in (L.RenderArgs, L.CompositeArgs, L.NetConfig, L.PassIO, L.Epilogue, L.RayBatchArgs,
+                                     L.TailArgs, L.AdamArgs)]
     assert got == want
 
 

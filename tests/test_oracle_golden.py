@@ -162,3 +162,25 @@ def test_transient_and_loss():
 def test_schedule_mult():
     assert O.schedule_mult(0.05) == 0 and O.schedule_mult(0.75) == 1
     assert abs(O.schedule_mult(0.3) - 0.5) < 1e-12
+
+
+def test_ray_batch():
+    """oracle/ray_batch.py against the real PhototourismDataset.__getitem__ + default_collate: every
+    field bit-exact (fp32 ops in the reference's order; the border rays have all-zero features)."""
+    from oracle import ray_batch as RB
+
+    g = load("ray_batch")
+    tables = {k[5:]: v for k, v in g.items() if k.startswith("tab__")}
+    out = RB.getitem_batch(tables, g["idx"])
+    want = {k[5:]: v for k, v in g.items() if k.startswith("out__")}
+    assert set(out) == set(want)
+    for k, v in want.items():
+        assert out[k].dtype == v.dtype and out[k].shape == v.shape, k
+        assert torch.equal(out[k], v), (k, float((out[k].double() - v.double()).abs().max()))
+    # the reference's border behaviour: a sample exactly on the last row or column gets zero weights
+    on_border = (tables["all_pxl_coords"][g["idx"]] == 1.0).any(1)
+    assert on_border.any() and (want["feats"][on_border] == 0).all()
+    # synthetic tables regenerate bit-identically (what the GPU tests rebuild at full size)
+    t2 = RB.synth_tables(3, 7, 9, 5, 12, seed=11)
+    for k, v in tables.items():
+        assert torch.equal(t2[k], v), k

@@ -438,3 +438,20 @@ def get_rays_bwd(c2w, directions, d_rays, d_c2w):
     single = 1 if c2w.dim() == 2 else 0
     check(lib().upnerf_get_rays_bwd(ptr(c2w), C.c_int(single), ptr(directions), _i64(directions.shape[0]),
                                     ptr(d_rays), ptr(d_c2w), stream_ptr()), "upnerf_get_rays_bwd")
+
+
+_RAY_BATCH_PTRS = ("idx", "ray_infos", "directions", "rgbs", "pxl_coords", "inv_depths", "feat_maps", "poses",
+                   "out_ray_infos", "out_directions", "out_img_idx", "out_c2w", "out_rgbs", "out_feats",
+                   "out_inv_depths", "status")
+
+
+class RayBatchArgs(C.Structure):
+    """Mirror of `upnerf_ray_batch_args`."""
+
+    _fields_ = ([("n_rays", C.c_int64), ("n_total", C.c_int64), ("n_images", C.c_int), ("feat_h", C.c_int),
+                 ("feat_w", C.c_int), ("feat_dim", C.c_int)]
+                + [(n, C.c_void_p) for n in _RAY_BATCH_PTRS])
+
+
+def ray_batch_gather(a: RayBatchArgs):
+    check(lib().upnerf_ray_batch_gather(C.byref(a), stream_ptr()), "upnerf_ray_batch_gather")
