@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -258,23 +259,28 @@ def main():
     # ---- leg 2: end to end from pinned host buffers -------------------------------------------
     pinned = [host_batch(R, 100 + 10 * rank + i, True) for i in range(n_batches)]
     h2d = sum(v.numel() * v.element_size() for v in pinned[0].values())
-    loss_host = torch.empty((), pin_memory=True)
+    from upnerf_b200.utils.pipeline import DelayedScalar, DevicePrefetcher
 
-    def e2e_step(i):
-        b = {k: v.to(dev, non_blocking=True) for k, v in pinned[i % n_batches].items()}
-        loss = system.training_step(b, i)
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller reads the loss every step
-        return float(loss_host)
+    def e2e_run(n, first):
+        """n steps fed from pinned host batches: the H2D copy of batch i+1 rides a copy stream under
+        step i, the loss of step i-1 is read on the host while step i runs (one D2H read per step; the
+        last one is drained before the region ends) -- all of it inside the timed region."""
+        losses, tail = [], DelayedScalar()
+        feed = DevicePrefetcher((pinned[(first + i) % n_batches] for i in range(n)), dev)
+        for i, b in enumerate(feed):
+            v = tail.push(system.training_step(b, first + i))
+            if v is not None:
+                losses.append(v)
+        losses.append(tail.last())
+        return losses
 
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(3, 0)
     barrier()
     e0.record()
-    for i in range(K):
-        e2e_step(i)
+    e2e_losses = e2e_run(K, 3)
     e1.record()
     barrier()
+    assert len(e2e_losses) == K and all(math.isfinite(x) for x in e2e_losses), "e2e: a step's loss was not read"
     ms_e2e = e0.elapsed_time(e1) / K
     t = torch.tensor([ms_e2e], device=dev)
     if world > 1:
@@ -353,7 +359,10 @@ def main():
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(args, args.precision),
         "e2e": {"value": world * R / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "pipeline": "public API: NeRFSystem.training_step fed by utils.pipeline.DevicePrefetcher (H2D of "
+                            "batch i+1 from pinned memory on a copy stream under step i) + DelayedScalar (loss of "
+                            "step i-1 read on the host during step i; last one drained inside the timed region)"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

@@ -346,6 +346,50 @@ def gen_ray_batch():
     _save("ray_batch", **arrays)
 
 
+def gen_pose_metric(ref_camera):
+    """utils/metric.py:10-21,35-77 (psnr, pose_metric and its stages) and utils/__init__.py:4-19
+    (extract_model_state_dict) from the real modules; `lpips` and `kornia.losses` (imported at module
+    level by utils/metric.py, not used by these functions) are stubbed."""
+    import tempfile
+
+    lp = types.ModuleType("lpips")
+    lp.LPIPS = lambda net="alex": None
+    sys.modules["lpips"] = lp
+    kl = types.ModuleType("kornia.losses")
+    kl.ssim = types.SimpleNamespace(ssim_loss=None)
+    sys.modules["kornia.losses"] = kl
+    sys.modules["kornia"].losses = kl
+    import utils as ref_utils
+    import utils.metric as ref_metric
+
+    g = torch.Generator().manual_seed(21)
+    n = 24
+    gt = ref_camera.lie.se3_to_SE3(torch.cat([0.6 * torch.randn(n, 3, generator=g), 2.0 * torch.randn(n, 3, generator=g)], 1))
+    # estimated poses = GT moved by a global similarity-free rigid motion + per-camera noise
+    glob = ref_camera.lie.se3_to_SE3(torch.tensor([[0.3, -0.2, 0.5, 1.0, -2.0, 0.5]]))[0]
+    noise = ref_camera.lie.se3_to_SE3(0.03 * torch.randn(n, 6, generator=g))
+    est = ref_camera.pose.compose([noise, gt, glob])
+    err, aligned, gt_parsed = ref_metric.pose_metric(est, gt)
+    assert err is not None
+    parsed = torch.stack([ref_metric.parse_raw_camera(p) for p in est], 0)
+    _, sim3 = ref_metric.prealign_cameras(parsed, gt_parsed)
+    img_a, img_b = torch.rand(1, 3, 12, 16, generator=g), torch.rand(1, 3, 12, 16, generator=g)
+    arrays = dict(est=est, gt=gt, err_R=err["R"], err_t=err["t"], aligned=aligned, gt_parsed=gt_parsed, parsed=parsed,
+                  sim3_R=sim3.R, sim3_t0=sim3.t0, sim3_t1=sim3.t1, sim3_s0=sim3.s0, sim3_s1=sim3.s1,
+                  img_a=img_a, img_b=img_b, psnr=ref_metric.psnr(img_a, img_b), mse=ref_metric.mse(img_a, img_b))
+    # extract_model_state_dict on a Lightning-format file
+    sd = {"nerf_coarse.xyz_encoding_1.0.weight": torch.ones(2), "nerf_coarse.progress": torch.zeros(1),
+          "nerf_fine.xyz_encoding_1.0.weight": torch.ones(3), "embedding_fine_a.weight": torch.ones(4),
+          "se3_refine.weight": torch.zeros(2, 6), "transient_net.embedding_t.weight": torch.ones(1)}
+    with tempfile.TemporaryDirectory() as d:
+        f = d + "/x.ckpt"
+        torch.save({"state_dict": sd, "hyper_parameters": {"max_steps": 10}}, f)
+        for name, ign in (("nerf_coarse", []), ("nerf_coarse", ["progress"]), ("embedding_fine_a", []), ("se3_refine", [])):
+            got = ref_utils.extract_model_state_dict(f, model_name=name, prefixes_to_ignore=ign)
+            arrays[f"ckptkeys__{name}__{len(ign)}"] = np.array(sorted(got), dtype="U64")
+    _save("pose_metric", **arrays)
+
+
 def main():
     ref_nerf, ref_rendering, ref_camera, ref_ray, ref_tnet, ref_losses = _import_reference()
     torch.set_num_threads(4)
@@ -357,6 +401,7 @@ def main():
     gen_render_rays(ref_nerf, ref_rendering)
     gen_tail(ref_tnet, ref_losses)
     gen_ray_batch()
+    gen_pose_metric(ref_camera)
 
 
 if __name__ == "__main__":

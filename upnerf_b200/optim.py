@@ -75,3 +75,17 @@ class FlatAdam(torch.optim.Optimizer):
         a.decay_mul = 1.0 - lr * float(group.get("weight_decay", 0.0))
         L.adam_step(a)
         return None
+
+    def state_dict(self):
+        """torch's optimiser state plus the per-class step counters (the bias corrections need them)."""
+        sd = super().state_dict()
+        sd["class_steps"] = dict(self.class_steps)
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        steps = state_dict.pop("class_steps", None)
+        super().load_state_dict(state_dict)
+        if steps is not None:
+            for k in self.class_steps:
+                self.class_steps[k] = int(steps.get(k, 0))
