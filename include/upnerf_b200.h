@@ -49,6 +49,9 @@ int upnerf_device_ok(void);
  * 7 heads, 8 pack, 9 trunk_fwd (fused), 10 trunk_bwd (fused).  work = flop of the launch
  * (2*M*N*K per GEMM), bytes = its algorithmic memory traffic (every operand touched once);
  * both 0 for families that do not declare them. */
+/* Measurement helper (tools/write_bw.py): fills `bytes` with an incompressible hash pattern using
+ * streaming 16-byte stores -- the write-only HBM ceiling the store-heavy kernels are judged against. */
+int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void* stream);
 long long upnerf_launch_count(void);
 void upnerf_profile_enable(int on);
 int upnerf_profile_collect(double* ms, long long* launches, double* work, double* bytes, int ncat);

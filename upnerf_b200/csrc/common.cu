@@ -147,3 +147,27 @@ int upnerf_device_ok(void) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ measurement helper
+namespace upnerf {
+namespace {
+__global__ void fill_pattern_kernel(uint4* dst, int64_t n16, uint32_t seed) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    uint32_t h = static_cast<uint32_t>(i) * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    uint4 v = make_uint4(h, h * 3266489917u, h ^ 0x9E3779B9u, h + static_cast<uint32_t>(i >> 7));
+    __stcs(dst + i, v);
+  }
+}
+}  // namespace
+}  // namespace upnerf
+
+extern "C" int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(dst && bytes > 0 && bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 UPNERF_ERR_BAD_SHAPE, "fill_pattern: 16-byte aligned buffer and size required");
+  fill_pattern_kernel<<<sm_count() * 16, 256, 0, as_stream(stream)>>>(static_cast<uint4*>(dst), bytes / 16, seed);
+  UPNERF_CHECK_LAUNCH("fill_pattern_kernel");
+  return UPNERF_OK;
+}

@@ -19,10 +19,14 @@
 // only idles for the first box of each layer.  Layers whose first K-chunk is the PE tile
 // (layer 1 and the skip layer) start even earlier, during the previous layer's epilogue.
 //
-// Measured (B200, M = 786432): 1.16 ms = 755 TFLOP/s with the activation stores, 0.79 ms
-// (1107 TFLOP/s) with the stores disabled -- the kernel sits between the HBM write roofline
-// (3.5 GB of activations per launch) and the shared-memory bandwidth the SS-mode UMMA needs
-// (12 KB per 128x256x16 MMA); see DESIGN.md section 5.
+// Measured (B200, M = 786432): 1.19 ms = 738 TFLOP/s with the activation stores, 0.79 ms
+// (1107 TFLOP/s) with the stores disabled.  ncu (profiles/r1_trunk_ncu_full.txt): tensor pipe active
+// 35 %, shared-memory pipes 26 % + 26 %, DRAM 38 %, issue slots 31 % -- no unit is saturated; the
+// kernel is bound by the serial MMA -> epilogue -> MMA chain of a tile (the MMAs of a layer-tile
+// take 2048 cycles of a ~5500-cycle period).  Tried and measured, none faster: a dedicated store
+// warp (epilogue never waits for a store to drain: 1.21 ms), per-thread st.global of the outputs
+// (1.84 ms), the cta_group::2 pair MMA (1.42 ms).  The fix is two tiles in flight per CTA so one
+// tile's epilogue runs under the other's MMAs; see DESIGN.md section 5.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -53,7 +57,8 @@ constexpr int kOffBias = kOffW + kWStages * kWBytes;
 constexpr int kOffHeadW = kOffBias + kNL * 256 * 4;
 constexpr int kOffHead = kOffHeadW + 256 * 4;
 constexpr int kOffBar = kOffHead + 4 * kTileM * 4;
-constexpr int kNumBars = 2 * kWStages + 4 + kChunks + 2;
+constexpr int kMaxWStages = 6;               // pair mode: six 16 KB half-chunk stages in the same 96 KB
+constexpr int kNumBars = 2 * kMaxWStages + 4 + kChunks + 2;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -92,7 +97,14 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // stream -- each loads one half (128 output features) of every weight chunk and TMA-multicasts
 // it into both CTAs, which halves the L2 -> shared-memory traffic (the first bound this kernel
 // hits: 1.06 MB of weights per 128-sample tile).
-template <int kCluster>
+//
+// k2Sm (kCluster = 2 only): the pair runs ONE tcgen05.mma.cta_group::2 per K step -- M = 256 (128 rows
+// from each CTA's activation tile), N = 256 with each CTA holding only ITS 128 output features of the
+// weight chunk (16 KB instead of 32 KB: the per-SM operand reads of every MMA drop from 12 KB to 8 KB
+// and the weight fill of shared memory halves).  The leader CTA's MMA thread issues for both; its
+// barriers collect both CTAs' TMA bytes (cp.async.bulk.tensor.cta_group::2) and both CTAs' epilogue
+// arrivals (remote mbarrier.arrive), and every commit is multicast to both CTAs.
+template <int kCluster, bool k2Sm = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -105,12 +117,15 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
   float* sHeadW = reinterpret_cast<float*>(smem + kOffHeadW);
   float* sHead = reinterpret_cast<float*>(smem + kOffHead);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  static_assert(!k2Sm || kCluster == 2, "the pair MMA needs a cluster of two");
+  constexpr int kStages = k2Sm ? kMaxWStages : kWStages;
+  constexpr int kStageBytes = k2Sm ? kWBytes / 2 : kWBytes;
   uint64_t* bar_wfull = bars;
-  uint64_t* bar_wempty = bars + kWStages;
-  uint64_t* bar_pefull = bars + 2 * kWStages;
-  uint64_t* bar_peempty = bars + 2 * kWStages + 2;
-  uint64_t* bar_act = bars + 2 * kWStages + 4;
-  uint64_t* bar_tfull = bars + 2 * kWStages + 4 + kChunks;
+  uint64_t* bar_wempty = bars + kMaxWStages;
+  uint64_t* bar_pefull = bars + 2 * kMaxWStages;
+  uint64_t* bar_peempty = bars + 2 * kMaxWStages + 2;
+  uint64_t* bar_act = bars + 2 * kMaxWStages + 4;
+  uint64_t* bar_tfull = bars + 2 * kMaxWStages + 4 + kChunks;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -128,19 +143,23 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     prefetch_tmap(&maps.w);
     prefetch_tmap(&maps.pe);
     for (int i = 0; i < kNL; ++i) prefetch_tmap(&maps.out[i]);
-    for (int i = 0; i < kWStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&bar_wfull[i], 1);
-      mbar_init(&bar_wempty[i], kCluster);
+      mbar_init(&bar_wempty[i], k2Sm ? 1 : kCluster);   // pair mode: one multicast commit from the leader
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_pefull[i], 1);
       mbar_init(&bar_peempty[i], 1);
       mbar_init(&bar_tfull[i], 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);  // one per output box: 8 warps of a set
+    // one per output box: the 8 warps of a set (pair mode: of both CTAs, on the leader's barrier)
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], k2Sm ? 16 : 8);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_holder);
+  if (warp == 1) {
+    if (k2Sm) tmem_alloc_2sm<512>(tmem_holder);
+    else tmem_alloc<512>(tmem_holder);
+  }
   if (warp >= 2) {
     const int t = threadIdx.x - 64;
     for (int i = t; i < kNL * 256; i += kEpiThreads) {
@@ -162,15 +181,21 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       uint32_t wph = 0;
       auto load_w = [&](int kcol) {
         mbar_wait(&bar_wempty[ws], wph ^ 1);
-        mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
-        if (kCluster == 1) {
+        if (k2Sm) {
+          // my 128 output features of the chunk, counted on the LEADER's barrier (which expects both halves)
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
+          tma_load_2d_2sm(sW + ws * kStageBytes, &maps.w, mapa_u32(smem_u32(&bar_wfull[ws]), 0), kcol,
+                          cta_rank * 128);
+        } else if (kCluster == 1) {
+          mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
           tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
         } else {
+          mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
           constexpr int kPart = kWBytes / kCluster;  // my share of the chunk: 256/kCluster features
           tma_load_2d_mc(sW + ws * kWBytes + cta_rank * kPart, &maps.w, &bar_wfull[ws], kcol,
                          cta_rank * (256 / kCluster), kMask);
         }
-        if (++ws == kWStages) {
+        if (++ws == kStages) {
           ws = 0;
           wph ^= 1;
         }
@@ -178,8 +203,14 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       auto load_pe = [&](int t, int tile) {
         const int slot = t & 1;
         mbar_wait(&bar_peempty[slot], ((t >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
-        tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
+        if (k2Sm) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bar_pefull[slot], 2 * kBoxBytes);
+          tma_load_2d_2sm(sPE + slot * kBoxBytes, &maps.pe, mapa_u32(smem_u32(&bar_pefull[slot]), 0), 0,
+                          tile * kTileM);
+        } else {
+          mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
+          tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
+        }
       };
       int t = 0;
       if (unit0 < num_units) load_pe(0, unit0 * kCluster + cta_rank);
@@ -198,16 +229,25 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
+    if (lane == 0 && (!k2Sm || cta_rank == 0)) {
+      const uint32_t idesc = umma_idesc_bf16(k2Sm ? 2 * kTileM : kTileM, 256, 0, 0);
       int ws = 0;
       uint32_t wph = 0;
       uint32_t act_ph = 0;
       uint32_t g = 0;  // layers issued so far (accumulator = g & 1)
       int t = 0;
       auto free_stage = [&](uint64_t* bar) {
-        if (kCluster == 1) mma_commit(bar);
+        if (k2Sm) mma_commit_2sm_mc(bar, kMask);
+        else if (kCluster == 1) mma_commit(bar);
         else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
+      };
+      auto commit_local = [&](uint64_t* bar) {   // pair mode: the peer's producer / epilogue wait on it too
+        if (k2Sm) mma_commit_2sm_mc(bar, kMask);
+        else mma_commit(bar);
+      };
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if (k2Sm) mma_bf16_ss_2sm(d, da, db, idesc, acc);
+        else mma_bf16_ss(d, da, db, idesc, acc);
       };
       for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
         const int slot = t & 1;
@@ -221,16 +261,16 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             mbar_wait(&bar_wfull[ws], wph);
             tc_fence_after_sync();
             const uint32_t a_addr = smem_u32(sPE + slot * kBoxBytes);
-            const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
+            const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                          umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
+              mma(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                  umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), accum);
               accum = 1;
             }
             free_stage(&bar_wempty[ws]);
-            if (L.pe_last) mma_commit(&bar_peempty[slot]);
-            if (++ws == kWStages) {
+            if (L.pe_last) commit_local(&bar_peempty[slot]);
+            if (++ws == kStages) {
               ws = 0;
               wph ^= 1;
             }
@@ -239,25 +279,26 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
               mbar_wait(&bar_wfull[ws], wph);
-              mbar_wait(&bar_act[b], act_ph);
+              if (k2Sm) mbar_wait_cluster(&bar_act[b], act_ph);
+              else mbar_wait(&bar_act[b], act_ph);
               tc_fence_after_sync();
               const uint32_t a_addr = smem_u32(sAct + b * kBoxBytes);
-              const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
+              const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                            umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
+                mma(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                    umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), accum);
                 accum = 1;
               }
               free_stage(&bar_wempty[ws]);
-              if (++ws == kWStages) {
+              if (++ws == kStages) {
                 ws = 0;
                 wph ^= 1;
               }
             }
             act_ph ^= 1;
           }
-          mma_commit(&bar_tfull[g & 1]);
+          commit_local(&bar_tfull[g & 1]);
         }
       }
     }
@@ -282,6 +323,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     const uint32_t sbias = smem_u32(sBias);
     const uint32_t sheadw = smem_u32(sHeadW);
     const uint32_t swz = row & 7;
+    // pair mode: "box written" goes to the leader CTA's barrier (its MMA thread issues for both CTAs)
+    const uint32_t act_bar0 = k2Sm ? mapa_u32(smem_u32(&bar_act[0]), 0) : 0;
     uint32_t g = 0;
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int tile = unit * kCluster + cta_rank;
@@ -354,7 +397,10 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             if (feeds) {
               tc_fence_before_sync();
               __syncwarp();
-              if (lane0) mbar_arrive(&bar_act[box]);  // one arrival per warp
+              if (lane0) {                             // one arrival per warp
+                if (k2Sm) mbar_arrive_cluster(act_bar0 + box * 8);
+                else mbar_arrive(&bar_act[box]);
+              }
             }
             // Box complete once both halves are: store it.  The set's other box is written next;
             // its previous store (the latest group of this leader) must have been read out.
@@ -385,7 +431,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
   if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still signal it
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
+    if (k2Sm) tmem_dealloc_2sm<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -664,6 +711,18 @@ int trunk_cluster_size() {
   v = (e && e[0] == '1') ? 1 : 2;
   return v;
 }
+// UPNERF_TRUNK_2SM=1 selects the cta_group::2 forward (one pair MMA per K step, see the kernel
+// comment).  Measured on B200 at M = 786,432: 1.42 ms against 1.19 ms for the default (pairs that
+// only share the weight stream by multicast and issue their own cta_group::1 MMAs) -- the layer
+// chain is serial per tile (MMA of layer l+1 waits for the epilogue of layer l, box by box), and the
+// cross-SM hops the pair adds to that handoff (remote mbarrier arrive -> cluster-scope wait; the
+// accumulator-ready commit fanned out to both CTAs) cost more than the halved operand traffic saves.
+// Kept as a tested variant: it becomes the right shape once two tiles are interleaved per CTA.
+// Read on every call so a test can toggle it.
+bool trunk_two_sm() {
+  const char* e = getenv("UPNERF_TRUNK_2SM");
+  return e && e[0] == '1' && trunk_cluster_size() == 2;
+}
 
 }  // namespace
 }  // namespace upnerf
@@ -706,13 +765,14 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   args.head_b = a->sigma_b;
   args.head_out = a->s_sigma;
   args.relu_mask = a->relu_mask;
-
   static bool attr_set = false;
   if (!attr_set) {
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
   const double flop = 2.0 * a->M * 256.0 * (64 + 7 * 256 + 320);
@@ -741,7 +801,8 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
+    if (trunk_two_sm()) UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2, true>, maps, args));
+    else UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
   }
   UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_kernel");
   return UPNERF_OK;
