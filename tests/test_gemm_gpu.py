@@ -203,16 +203,17 @@ def _trunk_reference(pe, ws, bs, sw, sb):
     return outs, sig
 
 
-@pytest.mark.parametrize("two_sm", ["0", "1"])
-@pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1])
-def test_mlp_trunk_fwd_fused(cuda_dev, M, two_sm, monkeypatch):
+@pytest.mark.parametrize("variant", ["dual", "multicast", "2sm"])
+@pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1, 128 * 148 * 5 + 77])
+def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
-    covers a single tile, a ragged last tile and >2 tiles per SM (pipeline wrap-around), for the
-    default kernel (CTA pairs sharing the weight stream) and the cta_group::2 variant
-    (UPNERF_TRUNK_2SM=1: one pair MMA per K step)."""
+    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around),
+    for the three forward kernels: dual-tile cta_group::2 (default), single-tile CTA pairs sharing the
+    weight stream by multicast (UPNERF_TRUNK_DUAL=0) and single-tile cta_group::2 (+UPNERF_TRUNK_2SM=1)."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_2SM", two_sm)
+    monkeypatch.setenv("UPNERF_TRUNK_DUAL", "1" if variant == "dual" else "0")
+    monkeypatch.setenv("UPNERF_TRUNK_2SM", "1" if variant == "2sm" else "0")
 
     g = torch.Generator(device="cpu").manual_seed(M)
     pe = _bf16(torch.randn(M, 64, generator=g))

@@ -171,3 +171,51 @@ extern "C" int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void
   UPNERF_CHECK_LAUNCH("fill_pattern_kernel");
   return UPNERF_OK;
 }
+
+// TMA-store ceiling probe (tools/write_bw.py): every CTA streams 128-row x 64-column bf16 boxes (16 KB,
+// the activation box of the fused trunk kernels) from shared memory to a [rows, ld] bf16 matrix with
+// up to four bulk stores in flight and no other work.  ld = 256 reproduces the trunk's pattern (128
+// rows of 128 B at a 512 B stride); ld = 64 makes every box one contiguous 16 KB run.
+#include "ptx_sm100.cuh"
+namespace upnerf {
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_row, int64_t n_boxes) {
+  extern __shared__ uint8_t probe_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(probe_raw) + 1023) & ~uintptr_t(1023));
+  for (int i = threadIdx.x; i < 4 * 16384 / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem)[i] = i * 2654435761u + blockIdx.x;
+  ptx::fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (int64_t b = blockIdx.x; b < n_boxes; b += gridDim.x, ++k) {
+      const int col = static_cast<int>(b % boxes_per_row) * 64;
+      const int row = static_cast<int>(b / boxes_per_row) * 128;
+      ptx::tma_store_2d(&map, smem + (k & 3) * 16384, col, row);
+      ptx::tma_store_commit();
+      ptx::tma_store_wait_read<3>();
+    }
+    ptx::tma_store_wait_all<0>();
+  }
+}
+}  // namespace
+}  // namespace upnerf
+
+extern "C" int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(dst && rows > 0 && rows % 128 == 0 && ld >= 64 && ld % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "tma_store_probe: rows %% 128 == 0 and ld %% 64 == 0 required");
+  CUtensorMap map;
+  UPNERF_TRY(make_tmap_bf16_2d(&map, dst, rows, ld, ld, 128, 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(tma_store_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           4 * 16384 + 1024));
+    attr_set = true;
+  }
+  const int bpr = static_cast<int>(ld / 64);
+  tma_store_probe_kernel<<<sm_count(), 128, 4 * 16384 + 1024, as_stream(stream)>>>(map, bpr, (rows / 128) * bpr);
+  UPNERF_CHECK_LAUNCH("tma_store_probe_kernel");
+  return UPNERF_OK;
+}
