@@ -220,6 +220,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = args.steps
