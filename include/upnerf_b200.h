@@ -53,8 +53,9 @@ int upnerf_device_ok(void);
  * streaming 16-byte stores -- the write-only HBM ceiling the store-heavy kernels are judged against. */
 int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void* stream);
 /* Measurement helper: TMA-store ceiling for 128 x 64 bf16 boxes written into a [rows, ld] bf16 matrix
- * (ld = 256: the fused trunk's activation-store pattern; ld = 64: contiguous 16 KB boxes). */
-int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, void* stream);
+ * (ld = 256: the fused trunk's activation-store pattern; ld = 64: contiguous 16 KB boxes), with 1..4
+ * bulk stores in flight per CTA (depth 1 exposes the issue -> shared-memory-read-done latency). */
+int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, int depth /* stores in flight, 1..4 */, void* stream);
 long long upnerf_launch_count(void);
 void upnerf_profile_enable(int on);
 int upnerf_profile_collect(double* ms, long long* launches, double* work, double* bytes, int ncat);

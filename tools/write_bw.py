@@ -31,5 +31,5 @@ ms=t(fillp); print("write-only hash pattern (st.global.cs v4) 4GiB: %.3f ms %.0f
 for ld in (256, 64, 320):
     rows = (y.numel() // 2 // ld) // 128 * 128
     def probe():
-        L.check(lib.upnerf_tma_store_probe(ctypes.c_void_p(y.data_ptr()), ctypes.c_int64(rows), ctypes.c_int64(ld), L.stream_ptr()), "probe")
+        L.check(lib.upnerf_tma_store_probe(ctypes.c_void_p(y.data_ptr()), ctypes.c_int64(rows), ctypes.c_int64(ld), ctypes.c_int(4), L.stream_ptr()), "probe")
     ms=t(probe); print("TMA store probe 128x64 bf16 boxes, ld=%d: %.3f ms %.0f GB/s"%(ld, ms, rows*ld*2/ms/1e6))

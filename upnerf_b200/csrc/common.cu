@@ -180,7 +180,7 @@ extern "C" int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void
 namespace upnerf {
 namespace {
 __global__ void __launch_bounds__(128, 1)
-tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_row, int64_t n_boxes) {
+tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_row, int64_t n_boxes, int depth) {
   extern __shared__ uint8_t probe_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(probe_raw) + 1023) & ~uintptr_t(1023));
   for (int i = threadIdx.x; i < 4 * 16384 / 4; i += blockDim.x)
@@ -194,7 +194,11 @@ tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_ro
       const int row = static_cast<int>(b / boxes_per_row) * 128;
       ptx::tma_store_2d(&map, smem + (k & 3) * 16384, col, row);
       ptx::tma_store_commit();
-      ptx::tma_store_wait_read<3>();
+      // depth = bulk stores allowed in flight (1: each store's shared-memory read is awaited alone)
+      if (depth >= 4) ptx::tma_store_wait_read<3>();
+      else if (depth == 3) ptx::tma_store_wait_read<2>();
+      else if (depth == 2) ptx::tma_store_wait_read<1>();
+      else ptx::tma_store_wait_read<0>();
     }
     ptx::tma_store_wait_all<0>();
   }
@@ -202,7 +206,7 @@ tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_ro
 }  // namespace
 }  // namespace upnerf
 
-extern "C" int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, void* stream) {
+extern "C" int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, int depth, void* stream) {
   using namespace upnerf;
   UPNERF_REQUIRE(dst && rows > 0 && rows % 128 == 0 && ld >= 64 && ld % 64 == 0, UPNERF_ERR_BAD_SHAPE,
                  "tma_store_probe: rows %% 128 == 0 and ld %% 64 == 0 required");
@@ -215,7 +219,7 @@ extern "C" int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, void*
     attr_set = true;
   }
   const int bpr = static_cast<int>(ld / 64);
-  tma_store_probe_kernel<<<sm_count(), 128, 4 * 16384 + 1024, as_stream(stream)>>>(map, bpr, (rows / 128) * bpr);
+  tma_store_probe_kernel<<<sm_count(), 128, 4 * 16384 + 1024, as_stream(stream)>>>(map, bpr, (rows / 128) * bpr, depth);
   UPNERF_CHECK_LAUNCH("tma_store_probe_kernel");
   return UPNERF_OK;
 }

@@ -8,7 +8,13 @@
 //
 // Output row layout (width 3+6L, padded with zeros to `ld_out`):
 //   [x0 x1 x2 | for c in 0..2: w_k sin(x_c f_k) k<L, w_k cos(x_c f_k) k<L],  f_k = fp32(pi) 2^k.
-// sin/cos arguments reach ~1e4, so the full-accuracy sincosf is used (no fast-math here).
+// sin/cos arguments reach ~1e4, so the full-accuracy sincosf is used (no fast-math here) -- in fp32
+// (validation) mode for every band.  In bf16 mode the kernels that feed / read bf16 tensors take ONE
+// full-accuracy sincosf per coordinate (argument pi x, |x| of a few units) and derive the other bands
+// by angle doubling, sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a: the error doubles per band
+// (~5e-5 absolute at band 9, below the 1.5e-4 the reference's own fp32 argument rounding moves the
+// top band, and 80x below bf16 resolution) and the instruction count drops ~6x -- these kernels
+// were bound by 60 sincosf calls per sample, not by HBM.
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -39,7 +45,14 @@ __global__ void c2f_weights_kernel(const float* __restrict__ progress, float sta
   w[k] = (1.f - cosf(__fmul_rn(t, kPi))) / 2.f;
 }
 
-template <typename T>
+// next band by angle doubling (bf16 paths only, see the file comment)
+__device__ __forceinline__ void double_angle(float& sn, float& cs) {
+  const float s2 = 2.f * sn * cs;
+  cs = fmaf(-2.f * sn, sn, 1.f);
+  sn = s2;
+}
+
+template <typename T, bool kFast = false>
 __device__ __forceinline__ void encode_row(const float x[3], int L, const float* __restrict__ bw,
                                            T* __restrict__ out, int ld_out) {
   const float kPi = 3.14159265358979323846f;
@@ -50,9 +63,11 @@ __device__ __forceinline__ void encode_row(const float x[3], int L, const float*
   for (int c = 0; c < 3; ++c) {
     float f = kPi;
     T* o = out + 3 + c * 2 * L;
+    float sn, cs;
+    if (kFast) sincosf(__fmul_rn(x[c], kPi), &sn, &cs);
     for (int k = 0; k < L; ++k) {
-      float sn, cs;
-      sincosf(__fmul_rn(x[c], f), &sn, &cs);
+      if (!kFast) sincosf(__fmul_rn(x[c], f), &sn, &cs);
+      else if (k > 0) double_angle(sn, cs);
       const float wk = bw[k];
       store_val(o + k, sn * wk);
       store_val(o + L + k, cs * wk);
@@ -102,7 +117,10 @@ __global__ void __launch_bounds__(128)
 points_posenc_fwd_tiled_kernel(const float* __restrict__ rays, const float* __restrict__ z, int64_t M, int S,
                                int L, const float* __restrict__ band_w, T* __restrict__ out, int64_t ld_row) {
   __shared__ float bw[kMaxL];
-  __shared__ float tile[128][65];
+  // staged in the OUTPUT type (bf16 rows are 132 B: twice the resident blocks per SM of an fp32 tile);
+  // odd word stride -> the row-per-thread writes are bank-conflict free
+  constexpr int kStride = sizeof(T) == 2 ? 66 : 65;
+  __shared__ T tile[128][kStride];
   if (threadIdx.x < L) bw[threadIdx.x] = band_w[threadIdx.x];
   __syncthreads();
   const int64_t m0 = blockIdx.x * 128ll;
@@ -114,20 +132,17 @@ points_posenc_fwd_tiled_kernel(const float* __restrict__ rays, const float* __re
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = __fadd_rn(ray[c], __fmul_rn(ray[3 + c], zz));
-    encode_row<float>(v, L, bw, &tile[threadIdx.x][0], 64);
+    encode_row<T, sizeof(T) == 2>(v, L, bw, &tile[threadIdx.x][0], 64);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 128 * 8; idx += 128) {
     const int row = idx >> 3, c8 = idx & 7;
     if (m0 + row >= M) continue;
-    const float* src = &tile[row][c8 * 8];
+    const T* src = &tile[row][c8 * 8];
     T* dst = out + (m0 + row) * ld_row + c8 * 8;
     if constexpr (sizeof(T) == 2) {
-      uint4 q;
-      __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) b[e] = __floats2bfloat162_rn(src[2 * e], src[2 * e + 1]);
-      *reinterpret_cast<uint4*>(dst) = q;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(src);   // rows are 4-byte aligned (stride 132 B)
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
       float4* d4 = reinterpret_cast<float4*>(dst);
       d4[0] = make_float4(src[0], src[1], src[2], src[3]);
@@ -161,9 +176,12 @@ points_posenc_bwd_kernel(const T* __restrict__ d_pe, int64_t ld_row, const float
       float dx = load_val(g + c);
       float f = kPi;
       const T* gc = g + 3 + c * 2 * L;
+      constexpr bool kFast = sizeof(T) == 2;
+      float sn, cs;
+      if (kFast) sincosf(__fmul_rn(xc, kPi), &sn, &cs);
       for (int k = 0; k < L; ++k) {
-        float sn, cs;
-        sincosf(__fmul_rn(xc, f), &sn, &cs);
+        if (!kFast) sincosf(__fmul_rn(xc, f), &sn, &cs);
+        else if (k > 0) double_angle(sn, cs);
         dx += bw[k] * f * (cs * load_val(gc + k) - sn * load_val(gc + L + k));
         f *= 2.f;
       }
@@ -248,10 +266,13 @@ points_posenc_bwd_row_kernel(const T* __restrict__ d_pe, int64_t ld_row, const f
       const float xc = __fadd_rn(o3[c], __fmul_rn(d3[c], zz));
       float dx = g[c];
       float f = kPi;
+      constexpr bool kFast = sizeof(T) == 2;
+      float sn, cs;
+      if (kFast) sincosf(__fmul_rn(xc, kPi), &sn, &cs);
 #pragma unroll
       for (int k = 0; k < L; ++k) {
-        float sn, cs;
-        sincosf(__fmul_rn(xc, f), &sn, &cs);
+        if (!kFast) sincosf(__fmul_rn(xc, f), &sn, &cs);
+        else if (k > 0) double_angle(sn, cs);
         dx += bw[k] * f * (cs * g[3 + c * 2 * L + k] - sn * g[3 + c * 2 * L + L + k]);
         f *= 2.f;
       }
