@@ -38,3 +38,14 @@ for ld in (256, 64):
         gbs = rows * ld * 2 / ms / 1e6
         bpc = gbs * 1e9 / 148 / 1.965e9
         print("ld=%d depth=%d: %.3f ms %.0f GB/s = %.1f B/clk/SM = %.0f cycles per 16 KB store" % (ld, depth, ms, gbs, bpc, 16384 / bpc))
+
+# L2-resident footprint, many passes inside one launch: the TMA engine's own store rate (no HBM limit)
+for mb in (16, 32):
+    rows = (mb * 1024 * 1024 // 2 // 256) // 128 * 128
+    reps = 63
+    def probe2():
+        L.check(lib.upnerf_tma_store_probe(ctypes.c_void_p(y.data_ptr()), ctypes.c_int64(rows), ctypes.c_int64(256),
+                                           ctypes.c_int(4 + (reps << 8)), L.stream_ptr()), "probe")
+    ms = t(probe2)
+    gbs = rows * 256 * 2 * (reps + 1) / ms / 1e6
+    print("L2-resident %d MB x %d passes, ld=256 depth=4: %.3f ms %.0f GB/s = %.1f B/clk/SM" % (mb, reps + 1, ms, gbs, gbs * 1e9 / 148 / 1.965e9))

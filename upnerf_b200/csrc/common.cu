@@ -189,6 +189,9 @@ tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, int boxes_per_ro
   __syncthreads();
   if (threadIdx.x == 0) {
     int k = 0;
+    const int reps = depth >> 8;     // high bits: passes over the footprint (L2-resident runs)
+    depth &= 255;
+    for (int rep = 0; rep <= reps; ++rep)
     for (int64_t b = blockIdx.x; b < n_boxes; b += gridDim.x, ++k) {
       const int col = static_cast<int>(b % boxes_per_row) * 64;
       const int row = static_cast<int>(b / boxes_per_row) * 128;

@@ -86,6 +86,14 @@ struct TrunkArgs {
   const float* head_b;
   float* head_out;
   uint32_t* relu_mask;  // [tiles][8 layers][8 chunks][128 rows] or nullptr
+  // lsu_store: a finished 64-column box goes to HBM as coalesced 16-byte st.global issued by the
+  // epilogue warps themselves (read back from the swizzled shared-memory box, 8 lanes per 128-byte
+  // row segment) instead of a TMA store.  The TMA unit of an SM moves ~27 B/clk (tools/
+  // tma_store_probe.py); with the weight stream (68 KB per layer and tile) AND the activation
+  // stores (64 KB) on it, it -- not the tensor pipe, shared memory or HBM -- paced the kernel.
+  int lsu_store;
+  __nv_bfloat16* out[kNL];
+  int64_t ld_out[kNL];
 };
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -229,7 +237,12 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!k2Sm || cta_rank == 0)) {
+    // The whole warp runs the loop (waits included) and ONE elected lane issues each tcgen05 op: with
+    // warp-uniform control flow the descriptor arithmetic stays in uniform registers.  A single
+    // diverged lane needed ~200 cycles of R2UR / ELECT / address math per MMA (ncu source view: 63 % of
+    // the issuing thread's samples in issue code, tensor pipe 35 % active) -- the issue thread, not
+    // the epilogue, paced the kernel.
+    if (!k2Sm || cta_rank == 0) {
       const uint32_t idesc = umma_idesc_bf16(k2Sm ? 2 * kTileM : kTileM, 256, 0, 0);
       int ws = 0;
       uint32_t wph = 0;
@@ -237,17 +250,32 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       uint32_t g = 0;  // layers issued so far (accumulator = g & 1)
       int t = 0;
       auto free_stage = [&](uint64_t* bar) {
-        if (k2Sm) mma_commit_2sm_mc(bar, kMask);
-        else if (kCluster == 1) mma_commit(bar);
-        else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
+        if (elect_one()) {
+          if (k2Sm) mma_commit_2sm_mc(bar, kMask);
+          else if (kCluster == 1) mma_commit(bar);
+          else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
+        }
+        __syncwarp();
       };
       auto commit_local = [&](uint64_t* bar) {   // pair mode: the peer's producer / epilogue wait on it too
-        if (k2Sm) mma_commit_2sm_mc(bar, kMask);
-        else mma_commit(bar);
+        if (elect_one()) {
+          if (k2Sm) mma_commit_2sm_mc(bar, kMask);
+          else mma_commit(bar);
+        }
+        __syncwarp();
       };
-      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-        if (k2Sm) mma_bf16_ss_2sm(d, da, db, idesc, acc);
-        else mma_bf16_ss(d, da, db, idesc, acc);
+      auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t& accum) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
+            const uint64_t db = umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128);
+            if (k2Sm) mma_bf16_ss_2sm(d, da, db, idesc, (k > 0) ? 1u : accum);
+            else mma_bf16_ss(d, da, db, idesc, (k > 0) ? 1u : accum);
+          }
+        }
+        __syncwarp();
+        accum = 1;
       };
       for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
         const int slot = t & 1;
@@ -262,12 +290,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             tc_fence_after_sync();
             const uint32_t a_addr = smem_u32(sPE + slot * kBoxBytes);
             const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              mma(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                  umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), accum);
-              accum = 1;
-            }
+            mma4(d_tmem, a_addr, b_addr, accum);
             free_stage(&bar_wempty[ws]);
             if (L.pe_last) commit_local(&bar_peempty[slot]);
             if (++ws == kStages) {
@@ -284,12 +307,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
               tc_fence_after_sync();
               const uint32_t a_addr = smem_u32(sAct + b * kBoxBytes);
               const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                    umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), accum);
-                accum = 1;
-              }
+              mma4(d_tmem, a_addr, b_addr, accum);
               free_stage(&bar_wempty[ws]);
               if (++ws == kStages) {
                 ws = 0;
@@ -379,20 +397,17 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
           sts128(box_row + ((s0 ^ swz) << 4), o[0]);
           sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
           if (want_mask) {
-            // ReLU mask of the stored (bf16) activations: bit e = column e of my 32-column chunk
-            const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
+            // ReLU mask: bit e = [column e of my 32-column chunk > 0].  v >= +0 after the ReLU, so its
+            // bit pattern is a non-negative integer and the sign of its negation is the predicate:
+            // one negate + one funnel shift per element
             uint32_t m16 = 0;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              m16 |= ((ow[e] & 0xFFFFu) ? 1u : 0u) << (2 * e);
-              m16 |= ((ow[e] >> 16) ? 1u : 0u) << (2 * e + 1);
-            }
+            for (int e = 15; e >= 0; --e)
+              m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
             mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
           }
           if (q & 1) {
             // my 32-column chunk of the box is written
-            if (want_mask)
-              args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
             fence_proxy_async_smem();   // my writes -> visible to the async proxy (MMA, TMA store)
             if (feeds) {
               tc_fence_before_sync();
@@ -402,9 +417,26 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
                 else mbar_arrive(&bar_act[box]);
               }
             }
+            // (after the hand-off: the proxy fence above is a full CTA membar and would otherwise wait
+            // for this global store's round trip before the MMA warp hears about the box)
+            if (want_mask)
+              args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
             // Box complete once both halves are: store it.  The set's other box is written next;
             // its previous store (the latest group of this leader) must have been read out.
-            if (store) {
+            if (store && args.lsu_store) {
+              named_bar_sync(set_bar, kSetThreads);   // the box is complete (both 32-column halves, all rows)
+              // my warp copies 16 of its 128 rows: lane -> (row = 4 i + lane / 8, 16-byte chunk = lane % 8)
+              const int w8 = ew & 7;
+              __nv_bfloat16* obase = args.out[l] + box * 64 + (lane & 7) * 8;
+              const uint32_t sbox = smem_u32(sAct) + box * kBoxBytes;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr2 = w8 * 16 + i * 4 + (lane >> 3);
+                const float4 vv = lds128(sbox + rr2 * 128 + ((((lane & 7) ^ (rr2 & 7))) << 4));
+                const int64_t gr = static_cast<int64_t>(tile) * kTileM + rr2;
+                if (gr < args.M) __stcs(reinterpret_cast<float4*>(obase + gr * args.ld_out[l]), vv);
+              }
+            } else if (store) {
               if (leader) tma_store_wait_read<0>();
               named_bar_sync(set_bar, kSetThreads);
               if (leader) {
@@ -801,6 +833,9 @@ struct BwdArgs {
   const float* d_ssig;
   const float* sig_w;
   const uint32_t* relu_mask;
+  int lsu_store;                 // see TrunkArgs::lsu_store
+  __nv_bfloat16* out[UPNERF_TRUNK_BWD_LAYERS];
+  int64_t ld_out[UPNERF_TRUNK_BWD_LAYERS];
 };
 
 template <int kCluster>
@@ -1008,11 +1043,25 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
               __syncwarp();
               if (lane0) mbar_arrive(&bar_act[box]);
             }
-            if (leader) tma_store_wait_read<0>();
-            named_bar_sync(set_bar, kSetThreads);
-            if (leader) {
-              tma_store_2d(&maps.out[j], sAct + box * kBoxBytes, box * 64, tile * kTileM);
-              tma_store_commit();
+            if (args.lsu_store) {
+              named_bar_sync(set_bar, kSetThreads);
+              const int w8 = ew & 7;
+              __nv_bfloat16* obase = args.out[j] + box * 64 + (lane & 7) * 8;
+              const uint32_t sbox = smem_u32(sAct) + box * kBoxBytes;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr2 = w8 * 16 + i * 4 + (lane >> 3);
+                const float4 vv = lds128(sbox + rr2 * 128 + ((((lane & 7) ^ (rr2 & 7))) << 4));
+                const int64_t gr = static_cast<int64_t>(tile) * kTileM + rr2;
+                if (gr < args.M) __stcs(reinterpret_cast<float4*>(obase + gr * args.ld_out[j]), vv);
+              }
+            } else {
+              if (leader) tma_store_wait_read<0>();
+              named_bar_sync(set_bar, kSetThreads);
+              if (leader) {
+                tma_store_2d(&maps.out[j], sAct + box * kBoxBytes, box * 64, tile * kTileM);
+                tma_store_commit();
+              }
             }
           }
         }
@@ -1102,6 +1151,17 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   args.head_b = a->sigma_b;
   args.head_out = a->s_sigma;
   args.relu_mask = a->relu_mask;
+  {
+    const char* e = getenv("UPNERF_TRUNK_LSU_STORE");
+    args.lsu_store = (e && e[0] == '0') ? 0 : 1;
+    for (int l = 0; l < kNL; ++l) {
+      args.out[l] = static_cast<__nv_bfloat16*>(a->out[l]);
+      args.ld_out[l] = a->ld_out[l];
+      // 16-byte vector stores need 8-element alignment of every row
+      if (a->out[l] && ((reinterpret_cast<uintptr_t>(a->out[l]) & 15) != 0 || (a->ld_out[l] & 7) != 0))
+        args.lsu_store = 0;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1193,9 +1253,18 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
   const int cluster = trunk_cluster_size();
   UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 256 / cluster, 64));
   UPNERF_TRY(make_tmap_bf16_2d(&maps.in, a->d_hf, a->M, 256, a->ld_dhf, kTileM, 64));
+  {
+    // Backward: faster alone (1.11 -> 1.03 ms at M = 786k) but not inside the train step, where the
+    // HBM-heavy leaf kernels of the side stream share the LSU path with it (1.10 -> 1.15 ms): opt-in.
+    const char* e = getenv("UPNERF_TRUNK_LSU_STORE");
+    args.lsu_store = (e && e[0] == '1') ? 1 : 0;
+  }
   for (int j = 0; j < kNLb; ++j) {
     UPNERF_REQUIRE(a->d_out[j], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: d_out[%d] missing", j);
     UPNERF_TRY(make_tmap_bf16_2d(&maps.out[j], a->d_out[j], a->M, 256, a->ld_dout[j], kTileM, 64));
+    args.out[j] = static_cast<__nv_bfloat16*>(a->d_out[j]);
+    args.ld_out[j] = a->ld_dout[j];
+    if ((reinterpret_cast<uintptr_t>(a->d_out[j]) & 15) != 0 || (a->ld_dout[j] & 7) != 0) args.lsu_store = 0;
   }
   static bool attr_set = false;
   if (!attr_set) {
