@@ -19,6 +19,7 @@
 // The aux operand (residual or ReLU mask) is TMA-loaded into the very smem box the result
 // is later stored from, one box ahead of its use.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -60,6 +61,12 @@ struct GemmArgs {
   int K;
   int num_tiles;
   upnerf_epilogue ep;
+  // lsu_store: finished 128 x 64 output boxes are copied out by the group's own threads (coalesced
+  // 16-byte st.global read back from the swizzled box) instead of a TMA store, which takes the
+  // output stream off the SM's TMA unit (~27 B/clk, shared with the operand loads)
+  int lsu_store;
+  __nv_bfloat16* C;
+  int64_t ldc;
 };
 
 __device__ __forceinline__ float softplus_ref(float x) {
@@ -334,15 +341,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *slot = out;
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (leader) {
-          tma_store_2d(&tmC, cbuf, ch * 64, tile * kBM);
-          tma_store_commit();
-          tma_store_wait_read<0>();  // box reusable; overlaps the other groups' work
+        if (args.lsu_store) {
+          named_bar_sync(bar_id, 128);
+          const int wq = ew & 3;
+          const uint32_t cb = smem_u32(cbuf);
+          __nv_bfloat16* obase = args.C + ch * 64 + (lane & 7) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr2 = wq * 32 + i * 4 + (lane >> 3);
+            const float4 vv = lds128(cb + rr2 * 128 + (((lane & 7) ^ (rr2 & 7)) << 4));
+            const int64_t gr = static_cast<int64_t>(tile) * kBM + rr2;
+            if (gr < args.M) __stcs(reinterpret_cast<float4*>(obase + gr * args.ldc), vv);
+          }
           if (has_aux) {
-            const int nb = next_box(t * nchunks + ch + 1);
-            if (nb >= 0) issue_aux(nb);
+            named_bar_sync(bar_id, 128);   // every thread has read its rows: the box may take the next aux tile
+            if (leader) {
+              const int nb = next_box(t * nchunks + ch + 1);
+              if (nb >= 0) issue_aux(nb);
+            }
+          }
+        } else {
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            tma_store_2d(&tmC, cbuf, ch * 64, tile * kBM);
+            tma_store_commit();
+            tma_store_wait_read<0>();  // box reusable; overlaps the other groups' work
+            if (has_aux) {
+              const int nb = next_box(t * nchunks + ch + 1);
+              if (nb >= 0) issue_aux(nb);
+            }
           }
         }
         ++qg;
@@ -407,6 +435,15 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   UPNERF_REQUIRE(!args.ep.ray_bias || args.ep.rows_per_ray > 0, UPNERF_ERR_BAD_SHAPE,
                  "gemm_bf16: ray_bias without rows_per_ray");
 
+  {
+    // opt-in: measured slower here (N = K = 256, M = 786k: 0.154 -> 0.196 ms) -- this kernel's TMA
+    // unit is not saturated (~19 B/clk per SM), so the copy-out only lengthens the epilogue
+    const char* e = getenv("UPNERF_GEMM_LSU_STORE");
+    args.lsu_store = (e && e[0] == '1') ? 1 : 0;
+    args.C = static_cast<__nv_bfloat16*>(C);
+    args.ldc = ldc;
+    if ((reinterpret_cast<uintptr_t>(C) & 15) != 0 || (ldc & 7) != 0) args.lsu_store = 0;
+  }
   CUtensorMap tmA, tmB, tmC, tmAux;
   UPNERF_TRY(make_tmap_bf16_2d(&tmA, A, M, K, lda, kBM, kBK));
   UPNERF_TRY(make_tmap_bf16_2d(&tmB, B, N, K, ldb, N, kBK));
