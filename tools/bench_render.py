@@ -48,7 +48,10 @@ def main():
     for chunk in [int(c) for c in args.chunks.split(",")]:
         system.hparams["val.chunk_size"] = chunk
         with torch.no_grad():
-            res = system(rays[:chunk * 2], feats[:chunk * 2], idx[:chunk * 2], 1.0, train=False)      # warm-up
+            # warm-up: ~0.25 M rays through the same chunk size (a fresh process's first launches, the
+            # caching allocator and the clocks settle; two chunks were not enough for 4096-ray chunks)
+            n_w = max(chunk * 2, min(R, 262144))
+            res = system(rays[:n_w], feats[:n_w], idx[:n_w], 1.0, train=False)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
