@@ -98,3 +98,40 @@ def test_adam_class_table():
     assert adam_class("transient_net.feat_encoder.0.weight") == "rgb"
     assert adam_class("depth_scale.weight") == "cand"
     assert adam_class("se3_refine.weight") == "always"
+
+
+def test_host_helpers_reject_cpu():
+    """The resident batcher and the host pipeline are CUDA-only like the rest of the path: they raise
+    instead of silently running somewhere else."""
+    import pytest
+    import torch
+
+    from oracle import ray_batch as RB
+    from upnerf_b200 import _lib as L
+    from upnerf_b200.datasets import RayBatcher
+    from upnerf_b200.utils.pipeline import DevicePrefetcher
+
+    t = RB.synth_tables(2, 4, 4, 3, 8, seed=1)
+    with pytest.raises(L.UpnerfError):
+        RayBatcher(t["all_ray_infos"], t["all_directions"], t["all_rgbs"], t["poses"], device="cpu")
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher([], "cpu")
+
+
+def test_ray_batch_oracle_edge_cases():
+    """Oracle restatement of the sample path: empty index set, repeated indices, the four corners."""
+    import torch
+
+    from oracle import ray_batch as RB
+
+    t = RB.synth_tables(2, 5, 7, 4, 6, seed=3)
+    empty = RB.getitem_batch(t, torch.zeros(0, dtype=torch.int64))
+    assert empty["feats"].shape == (0, 6) and empty["c2w"].shape == (0, 3, 4)
+    n = 5 * 7
+    corners = torch.tensor([0, 6, n - 7, n - 1, n, 2 * n - 1, 3, 3])
+    out = RB.getitem_batch(t, corners)
+    assert torch.equal(out["img_idx"], torch.tensor([0, 0, 0, 0, 1, 1, 0, 0]))
+    assert torch.equal(out["feats"][6], out["feats"][7])
+    # top-left corner = the map's (0, 0) pixel exactly; any sample on the last row / column = 0
+    assert torch.equal(out["feats"][0], t["feat_maps"][0, 0, 0])
+    assert (out["feats"][[1, 2, 3, 5]] == 0).all()
