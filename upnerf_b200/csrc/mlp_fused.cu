@@ -343,13 +343,24 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     const uint32_t swz = row & 7;
     // pair mode: "box written" goes to the leader CTA's barrier (its MMA thread issues for both CTAs)
     const uint32_t act_bar0 = k2Sm ? mapa_u32(smem_u32(&bar_act[0]), 0) : 0;
+    // copy-out mapping (lsu_store): lane -> row cp_row0 + 4 i (i = 0..3) of the box, 16-byte chunk lane % 8.
+    // Row r keeps chunk c at position c ^ (r & 7); (r & 7) = lane / 8 for even i and lane / 8 + 4 for odd i.
+    const int cp_row0 = (ew & 7) * 16 + (lane >> 3);
+    const uint32_t cp_x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
+    const uint32_t cp_soff_even = cp_row0 * 128 + cp_x0;
+    const uint32_t cp_soff_odd = cp_row0 * 128 + (cp_x0 ^ 64u);
     uint32_t g = 0;
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int tile = unit * kCluster + cta_rank;
       const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
+      const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;   // rows of this tile that exist
       for (int l = 0; l < kNL; ++l, ++g) {
         const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
         const int store = args.layer[l].store;
+        // copy-out of this layer's boxes: where my lane's rows go (see cp_row0 above)
+        const int64_t out_ld = args.ld_out[l];
+        __nv_bfloat16* out_lane =
+            store ? args.out[l] + (static_cast<int64_t>(tile) * kTileM + cp_row0) * out_ld + (lane & 7) * 8 : nullptr;
         mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
@@ -426,16 +437,16 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             if (store && args.lsu_store) {
               named_bar_sync(set_bar, kSetThreads);   // the box is complete (both 32-column halves, all rows)
               // my warp copies 16 of its 128 rows: lane -> (row = 4 i + lane / 8, 16-byte chunk = lane % 8)
-              const int w8 = ew & 7;
-              __nv_bfloat16* obase = args.out[l] + box * 64 + (lane & 7) * 8;
+              // my warp copies 16 of the box's 128 rows, 4 rows x 128 B per instruction; all four loads
+              // are issued before the stores
               const uint32_t sbox = smem_u32(sAct) + box * kBoxBytes;
+              float4 vv[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr2 = w8 * 16 + i * 4 + (lane >> 3);
-                const float4 vv = lds128(sbox + rr2 * 128 + ((((lane & 7) ^ (rr2 & 7))) << 4));
-                const int64_t gr = static_cast<int64_t>(tile) * kTileM + rr2;
-                if (gr < args.M) __stcs(reinterpret_cast<float4*>(obase + gr * args.ld_out[l]), vv);
-              }
+              for (int i = 0; i < 4; ++i) vv[i] = lds128(sbox + ((i & 1) ? cp_soff_odd : cp_soff_even) + i * 512);
+              __nv_bfloat16* orow = out_lane + box * 64;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (cp_row0 + i * 4 < rows_left) __stcs(reinterpret_cast<float4*>(orow + i * 4 * out_ld), vv[i]);
             } else if (store) {
               if (leader) tma_store_wait_read<0>();
               named_bar_sync(set_bar, kSetThreads);
