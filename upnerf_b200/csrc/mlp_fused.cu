@@ -12,6 +12,8 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x 256 x 16).
 //   warps 2..17 epilogue, two sets of eight warps (set s owns output boxes s and s+2):
 //               thread = one output row x 16 of the 32 columns of a chunk.
+//   warps 18,19 copy-out (default store path): wait for "box written", read their 64 rows of the
+//               swizzled box and stream them to HBM with coalesced 16-byte st.global.
 //
 // Pipelining inside a tile: the accumulator is double buffered in TMEM (2 x 256 columns), and
 // the epilogue releases its output box by box (64 columns, one mbarrier each), so the MMAs of
@@ -48,6 +50,8 @@ constexpr int kWBytes = 256 * 128;        // 256 output features x 64 K columns
 constexpr int kSetThreads = 256;           // one epilogue set: 8 warps
 constexpr int kEpiThreads = 2 * kSetThreads;
 constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kCopyWarps = 2;                       // forward, lsu_store == 2: dedicated copy-out warps
+constexpr int kThreadsF = kThreads + 32 * kCopyWarps;
 constexpr int kChunks = 8;                // 32-column chunks per 256-wide layer
 
 constexpr int kOffAct = 0;
@@ -58,7 +62,7 @@ constexpr int kOffHeadW = kOffBias + kNL * 256 * 4;
 constexpr int kOffHead = kOffHeadW + 256 * 4;
 constexpr int kOffBar = kOffHead + 4 * kTileM * 4;
 constexpr int kMaxWStages = 6;               // pair mode: six 16 KB half-chunk stages in the same 96 KB
-constexpr int kNumBars = 2 * kMaxWStages + 4 + kChunks + 2;
+constexpr int kNumBars = 2 * kMaxWStages + 4 + kChunks + 2 + 8;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -113,7 +117,7 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // barriers collect both CTAs' TMA bytes (cp.async.bulk.tensor.cta_group::2) and both CTAs' epilogue
 // arrivals (remote mbarrier.arrive), and every commit is multicast to both CTAs.
 template <int kCluster, bool k2Sm = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsF, 1)
 mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -134,6 +138,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
   uint64_t* bar_peempty = bars + 2 * kMaxWStages + 2;
   uint64_t* bar_act = bars + 2 * kMaxWStages + 4;
   uint64_t* bar_tfull = bars + 2 * kMaxWStages + 4 + kChunks;
+  uint64_t* bar_st = bar_tfull + 2;        // [4] lsu_store == 2: box written (8 warps of its set) -> copy-out warps
+  uint64_t* bar_stfree = bar_st + 4;       // [4] box copied out (kCopyWarps arrivals) -> may be overwritten
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -162,13 +168,17 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     }
     // one per output box: the 8 warps of a set (pair mode: of both CTAs, on the leader's barrier)
     for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], k2Sm ? 16 : 8);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bar_st[i], 8);
+      mbar_init(&bar_stfree[i], kCopyWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
     if (k2Sm) tmem_alloc_2sm<512>(tmem_holder);
     else tmem_alloc<512>(tmem_holder);
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 18) {
     const int t = threadIdx.x - 64;
     for (int i = t; i < kNL * 256; i += kEpiThreads) {
       const float* b = args.bias[i >> 8];
@@ -320,6 +330,52 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
         }
       }
     }
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------ copy-out warps (lsu_store == 2)
+    // Each of the kCopyWarps warps owns 128 / kCopyWarps rows of every box: it waits for "box written",
+    // reads its rows out of the swizzled box (4 rows x 128 B per instruction, eight loads in flight)
+    // and streams them to HBM with coalesced 16-byte stores, then releases the box.  The epilogue warps
+    // neither store nor meet at a per-box barrier; they only check that the box they are about to
+    // overwrite was released (a whole layer earlier).
+    if (args.lsu_store == 2) {
+      const int cw = warp - 18;
+      constexpr int kRowsPer = kTileM / kCopyWarps;           // 64
+      const int r0 = cw * kRowsPer + (lane >> 3);              // my first row; rows r0 + 4 i
+      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
+      const uint32_t so_even = r0 * 128 + x0, so_odd = r0 * 128 + (x0 ^ 64u);
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int tile = unit * kCluster + cta_rank;
+        const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;
+        for (int l = 0; l < kNL; ++l) {
+          if (!args.layer[l].store) continue;
+          const int64_t ldo = args.ld_out[l];
+          __nv_bfloat16* o0 = args.out[l] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
+          for (int b = 0; b < 4; ++b) {
+            mbar_wait(&bar_st[b], ph);
+            const uint32_t sbox = smem_u32(sAct) + b * kBoxBytes;
+            __nv_bfloat16* ob = o0 + b * 64;
+#pragma unroll
+            for (int h = 0; h < kRowsPer / 32; ++h) {          // 8 x (4 rows) per pass
+              float4 vv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                vv[i] = lds128(sbox + ((i & 1) ? so_odd : so_even) + (h * 8 + i) * 512);
+              if (h == kRowsPer / 32 - 1) {
+                // all my reads of this box are in registers: the epilogue may overwrite it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_stfree[b]);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (r0 + (h * 8 + i) * 4 < rows_left)
+                  __stcs(reinterpret_cast<float4*>(ob + static_cast<int64_t>((h * 8 + i) * 4) * ldo), vv[i]);
+            }
+          }
+          ph ^= 1;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue warps
     // Two sets of eight warps.  Set s owns the 64-column output boxes s and s+2 of every layer;
@@ -350,6 +406,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     const uint32_t cp_soff_even = cp_row0 * 128 + cp_x0;
     const uint32_t cp_soff_odd = cp_row0 * 128 + (cp_x0 ^ 64u);
     uint32_t g = 0;
+    uint32_t nst = 0;   // lsu_store == 2: stored layers so far (= releases seen per box)
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int tile = unit * kCluster + cta_rank;
       const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
@@ -373,6 +430,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
         for (int q = 0; q < 4; ++q) {
           const int box = set + (q & 2);                  // q = 0,1: box s; q = 2,3: box s+2
           const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+          // copy-out warps: the previous contents of this box must have been read out before my first write
+          if (args.lsu_store == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[box], (nst - 1) & 1);
           tmem_ld_wait_dep(r[q & 1]);
           if (q < 3) {
             const int nbox = set + ((q + 1) & 2);
@@ -434,7 +493,10 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
               args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
             // Box complete once both halves are: store it.  The set's other box is written next;
             // its previous store (the latest group of this leader) must have been read out.
-            if (store && args.lsu_store) {
+            if (store && args.lsu_store == 2) {
+              __syncwarp();
+              if (lane0) mbar_arrive(&bar_st[box]);   // the copy-out warps take it from here
+            } else if (store && args.lsu_store) {
               named_bar_sync(set_bar, kSetThreads);   // the box is complete (both 32-column halves, all rows)
               // my warp copies 16 of its 128 rows: lane -> (row = 4 i + lane / 8, 16-byte chunk = lane % 8)
               // my warp copies 16 of the box's 128 rows, 4 rows x 128 B per instruction; all four loads
@@ -457,6 +519,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             }
           }
         }
+        if (store) ++nst;
         if (head) {
           sHead[grp * kTileM + row] = hacc;
           named_bar_sync(4, kEpiThreads);
@@ -1163,8 +1226,9 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   args.head_out = a->s_sigma;
   args.relu_mask = a->relu_mask;
   {
+    // 0: TMA stores; 1: the epilogue warps copy their set's box out; 2: two dedicated copy-out warps
     const char* e = getenv("UPNERF_TRUNK_LSU_STORE");
-    args.lsu_store = (e && e[0] == '0') ? 0 : 1;
+    args.lsu_store = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
     for (int l = 0; l < kNL; ++l) {
       args.out[l] = static_cast<__nv_bfloat16*>(a->out[l]);
       args.ld_out[l] = a->ld_out[l];
@@ -1193,7 +1257,7 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   LaunchScope scope(kCatTrunkFwd, as_stream(stream), flop, bytes);
   if (cluster == 1) {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-    mlp_trunk_fwd_kernel<1><<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(maps, args);
+    mlp_trunk_fwd_kernel<1><<<grid, kThreadsF, kSmemBytes, as_stream(stream)>>>(maps, args);
   } else if (trunk_dual()) {
     const int64_t units = ceil_div64(tiles, 4);
     const int max_clusters = sm_count() / 2;
@@ -1219,7 +1283,7 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsF);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute attr[1];
