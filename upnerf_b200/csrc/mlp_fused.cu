@@ -893,7 +893,7 @@ constexpr int kOffActB = kOffIn + kActBytes;
 constexpr int kOffWB = kOffActB + kActBytes;
 constexpr int kOffSigW = kOffWB + kWStages * kWBytes;
 constexpr int kOffBarB = kOffSigW + 256 * 4;
-constexpr int kNumBarsB = 2 * kWStages + 2 + 4 + 2;
+constexpr int kNumBarsB = 2 * kWStages + 2 + 4 + 2 + 8;
 constexpr int kOffTmemB = kOffBarB + kNumBarsB * 8;
 constexpr int kSmemBytesB = kOffTmemB + 16 + 1024;
 static_assert(kSmemBytesB <= 232448, "shared memory budget exceeded");
@@ -913,7 +913,7 @@ struct BwdArgs {
 };
 
 template <int kCluster>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsF, 1)
 mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -929,6 +929,8 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
   uint64_t* bar_inempty = bars + 2 * kWStages + 1;
   uint64_t* bar_act = bars + 2 * kWStages + 2;
   uint64_t* bar_tfull = bars + 2 * kWStages + 6;
+  uint64_t* bar_st = bar_tfull + 2;        // [4] lsu_store == 2: box written -> copy-out warps (see forward)
+  uint64_t* bar_stfree = bar_st + 4;       // [4] box copied out -> may be overwritten
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmemB);
 
   const int warp = threadIdx.x >> 5;
@@ -951,10 +953,14 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
     mbar_init(bar_inempty, 1);
     for (int i = 0; i < 2; ++i) mbar_init(&bar_tfull[i], 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bar_st[i], 8);
+      mbar_init(&bar_stfree[i], kCopyWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_holder);
-  if (warp >= 2)
+  if (warp >= 2 && warp < 18)
     for (int i = threadIdx.x - 64; i < 256; i += kEpiThreads) sSigW[i] = args.sig_w ? args.sig_w[i] : 0.f;
   tc_fence_before_sync();
   __syncthreads();
@@ -1043,6 +1049,45 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
         }
       }
     }
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------ copy-out warps (lsu_store == 2, see forward)
+    if (args.lsu_store == 2) {
+      const int cw = warp - 18;
+      constexpr int kRowsPer = kTileM / kCopyWarps;
+      const int r0 = cw * kRowsPer + (lane >> 3);
+      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
+      const uint32_t so_even = r0 * 128 + x0, so_odd = r0 * 128 + (x0 ^ 64u);
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        const int tile = unit * kCluster + cta_rank;
+        const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;
+        for (int j = 0; j < kNLb; ++j) {
+          const int64_t ldo = args.ld_out[j];
+          __nv_bfloat16* o0 = args.out[j] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
+          for (int bx = 0; bx < 4; ++bx) {
+            mbar_wait(&bar_st[bx], ph);
+            const uint32_t sbox = smem_u32(sAct) + bx * kBoxBytes;
+            __nv_bfloat16* ob = o0 + bx * 64;
+#pragma unroll
+            for (int h = 0; h < kRowsPer / 32; ++h) {
+              float4 vv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                vv[i] = lds128(sbox + ((i & 1) ? so_odd : so_even) + (h * 8 + i) * 512);
+              if (h == kRowsPer / 32 - 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_stfree[bx]);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (r0 + (h * 8 + i) * 4 < rows_left)
+                  __stcs(reinterpret_cast<float4*>(ob + static_cast<int64_t>((h * 8 + i) * 4) * ldo), vv[i]);
+            }
+          }
+          ph ^= 1;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue warps (see forward)
     const int ew = warp - 2;
@@ -1058,6 +1103,7 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
     const uint32_t ssigw = smem_u32(sSigW);
     const uint32_t swz = row & 7;
     uint32_t g = 0;
+    uint32_t nst = 0;   // lsu_store == 2: layers stored so far (= releases seen per box)
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int tile = unit * kCluster + cta_rank;
       const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
@@ -1079,6 +1125,7 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
         for (int q = 0; q < 4; ++q) {
           const int box = set + (q & 2);
           const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+          if (args.lsu_store == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[box], (nst - 1) & 1);
           tmem_ld_wait_dep(r[q & 1]);
           if (q < 3) {
             const int nbox = set + ((q + 1) & 2);
@@ -1117,7 +1164,10 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
               __syncwarp();
               if (lane0) mbar_arrive(&bar_act[box]);
             }
-            if (args.lsu_store) {
+            if (args.lsu_store == 2) {
+              __syncwarp();
+              if (lane0) mbar_arrive(&bar_st[box]);
+            } else if (args.lsu_store) {
               named_bar_sync(set_bar, kSetThreads);
               const int w8 = ew & 7;
               __nv_bfloat16* obase = args.out[j] + box * 64 + (lane & 7) * 8;
@@ -1139,6 +1189,7 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
             }
           }
         }
+        ++nst;
       }
     }
     if (leader) tma_store_wait_all<0>();
@@ -1329,10 +1380,11 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
   UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 256 / cluster, 64));
   UPNERF_TRY(make_tmap_bf16_2d(&maps.in, a->d_hf, a->M, 256, a->ld_dhf, kTileM, 64));
   {
-    // Backward: faster alone (1.11 -> 1.03 ms at M = 786k) but not inside the train step, where the
-    // HBM-heavy leaf kernels of the side stream share the LSU path with it (1.10 -> 1.15 ms): opt-in.
-    const char* e = getenv("UPNERF_TRUNK_LSU_STORE");
-    args.lsu_store = (e && e[0] == '1') ? 1 : 0;
+    // Backward: the epilogue-copy variant (1) is faster alone (1.11 -> 1.03 ms at M = 786k) but not inside
+    // the train step (1.10 -> 1.15 ms next to the side stream's HBM-heavy leaves); the copy-out warps (2)
+    // gain there as well (1.18 -> 1.05 ms).
+    const char* e = getenv("UPNERF_TRUNK_BWD_STORE");     // 0: TMA stores, 1: epilogue copy, 2: copy-out warps (default)
+    args.lsu_store = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
   }
   for (int j = 0; j < kNLb; ++j) {
     UPNERF_REQUIRE(a->d_out[j], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: d_out[%d] missing", j);
@@ -1355,7 +1407,7 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
   LaunchScope scope(kCatTrunkBwd, as_stream(stream), flop, bytes);
   if (cluster == 1) {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-    mlp_trunk_bwd_kernel<1><<<grid, kThreads, kSmemBytesB, as_stream(stream)>>>(maps, args);
+    mlp_trunk_bwd_kernel<1><<<grid, kThreadsF, kSmemBytesB, as_stream(stream)>>>(maps, args);
   } else {
     const int64_t units = ceil_div64(tiles, 2);
     const int max_clusters = sm_count() / 2;
@@ -1363,7 +1415,7 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsF);
     cfg.dynamicSmemBytes = kSmemBytesB;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute attr[1];
