@@ -390,6 +390,265 @@ def gen_pose_metric(ref_camera):
     _save("pose_metric", **arrays)
 
 
+# ---------------------------------------------------------------------------------------------
+# The REAL NeRFSystem.training_step / NeRFSystemOptimize.training_step
+# ---------------------------------------------------------------------------------------------
+TRAIN_CASE = dict(R=48, S=12, NI=12, n_img=6, max_steps=10, n_steps=7, seed=11)
+
+
+def _import_systems():
+    """models/nerf_system.py + models/nerf_system_optmize.py under the stubs of SURVEY.md Appendix A:
+    absent third-party packages (pytorch_lightning, lpips, kornia.losses, matplotlib, imageio,
+    mpl_toolkits) become empty modules; `LightningModule` is a minimal manual-optimisation shim whose
+    `global_step` counts optimizer steps the way Lightning's manual-optimisation loop does (one per
+    `optimizers()[i].step()`), which is what `progress = global_step / (2 * max_steps)`
+    (models/nerf_system.py:220-226) relies on.  No reference source is modified."""
+
+    def stub(name, **kw):
+        if name in sys.modules and not kw:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    kl = stub("kornia.losses", ssim=types.SimpleNamespace(ssim_loss=None))
+    sys.modules["kornia"].losses = kl
+    stub("lpips", LPIPS=lambda net="alex": None)
+    for name in ("imageio", "matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        stub(name)
+    stub("mpl_toolkits.mplot3d.art3d", Poly3DCollection=None)
+
+    class LightningModule(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.global_step = 0
+            self.logged = {}
+
+        def save_hyperparameters(self, h):
+            self.hparams = dict(h)
+
+        def log(self, k, v, **kw):
+            self.logged[k] = v
+
+        def manual_backward(self, loss):
+            loss.backward()
+
+        def optimizers(self):
+            return self._opts if len(self._opts) > 1 else self._opts[0]
+
+        def lr_schedulers(self):
+            return self._scheds if len(self._scheds) > 1 else self._scheds[0]
+
+    stub("pytorch_lightning", LightningModule=LightningModule)
+    stub("pytorch_lightning.utilities")
+    stub("pytorch_lightning.utilities.types", EPOCH_OUTPUT=None)
+    import configs.config as ref_config
+    import models.nerf_system as ref_sys
+    import models.nerf_system_optmize as ref_opt
+
+    return ref_config, ref_sys, ref_opt
+
+
+class _LightningOptimizer:
+    """What `self.optimizers()[i]` is under Lightning: forwards to the torch optimiser and advances the
+    module's global_step once per step() (manual optimisation)."""
+
+    def __init__(self, system, optimizer):
+        self.system, self.optimizer = system, optimizer
+        self.param_groups = optimizer.param_groups
+
+    def zero_grad(self):
+        self.optimizer.zero_grad()
+
+    def step(self):
+        self.optimizer.step()
+        self.system.global_step += 1
+
+
+def _train_state(case):
+    """Initial full-width state (same recipe as tests/test_train_step_gpu.py:make_system)."""
+    from . import synth
+    from .train_step import KW
+    from .upnerf_oracle import NerfConfig
+
+    n_img, seed = case["n_img"], case["seed"]
+    cfgs = {"nerf_coarse": NerfConfig(typ="coarse", **KW), "nerf_fine": NerfConfig(typ="fine", **KW)}
+    sd = {}
+    for k, cfg in cfgs.items():
+        for pn, v in synth.nerf_state(cfg, seed + (k == "nerf_fine")).items():
+            sd[f"{k}.{pn}"] = v
+    for k, v in synth.embeddings(n_img, cfgs["nerf_coarse"], seed).items():
+        sd[f"embedding_{k}.weight"] = v * 0.3
+    for pn, v in synth.transient_state(n_img, seed).items():
+        sd[f"transient_net.{pn}"] = v
+    sd["se3_refine.weight"] = synth.uniform((n_img, 6), seed + 5, -0.02, 0.02)
+    sd["depth_scale.weight"] = synth.uniform((n_img, 2), seed + 6, -0.05, 0.05)
+    return cfgs, sd
+
+
+def _build_system(cls, ref_config, case, extra=None):
+    hp = ref_config.get_from_path(REF + "/configs/brandenburg_gate.yaml")
+    hp.update({"nerf.N_samples": case["S"], "nerf.N_importance": case["NI"], "max_steps": case["max_steps"],
+               "debug": True})
+    hp.update(extra or {})
+    system = cls(hp)
+    system.train_dataset = types.SimpleNamespace(N_images_train=case["n_img"], N_images_test=case["n_img"],
+                                                 white_back=False)
+    # model_setup() moves the two pose tables `.to("cuda")` (models/nerf_system.py:399-402); this
+    # container has no GPU, so device moves are no-ops while it runs
+    orig_to = torch.nn.Module.to
+    torch.nn.Module.to = lambda self, *a, **k: self
+    try:
+        ref_sys_cls = [c for c in cls.__mro__ if c.__name__ == "NeRFSystem"][0]
+        ref_sys_cls.model_setup(system)
+    finally:
+        torch.nn.Module.to = orig_to
+    system.log_pose = lambda: None
+    return system
+
+
+def _wire(system):
+    out = system.configure_optimizers()
+    opts, scheds = out if isinstance(out, tuple) else (out, [])
+    system._opts = [_LightningOptimizer(system, o) for o in opts]
+    system._scheds = [s["scheduler"] for s in scheds]
+
+
+def _replay_rng(seed, R, S, NI, m, cand=True):
+    """The reference's draw order inside render_rays: coarse perturbation, then one
+    torch.rand per sample_pdf call."""
+    torch.manual_seed(seed)
+    out = {"perturb_rand": torch.rand(R, S)}
+    if cand and 0 < m < 1:
+        ns = round(m * NI)
+        out["u0"], out["u1"] = torch.rand(R, NI - ns), torch.rand(R, ns)
+    else:
+        out["u0"] = torch.rand(R, NI)
+    return out
+
+
+def _state_digest(prefix, sd, arrays):
+    for k, v in sd.items():
+        v = v.detach().float()
+        arrays[f"{prefix}__norm__{k}"] = v.double().norm().float()
+        flat = v.reshape(-1)
+        arrays[f"{prefix}__head__{k}"] = flat[:64].clone()
+        if flat.numel() <= 4096:
+            arrays[f"{prefix}__full__{k}"] = v.clone()
+
+
+def gen_train_step(name="train_step_real", start=0.0, n_steps=None):
+    """Real `NeRFSystem.training_step` calls (models/nerf_system.py:150-229) with max_steps = 10: from
+    `start` = 0 seven steps see progress = 0, .1, ..., .6 and cross phase 0 -> 1 -> 2
+    (candidate_schedule [0.1, 0.5]); two Adam optimisers + two ExponentialLR schedulers from the real
+    configure_optimizers (:41-73).  The short `start` = 0.3 / 0.6 runs give phase-1 / phase-2 steps from a
+    fresh optimiser state (no accumulated Adam drift), so they can be compared tightly."""
+    from . import synth
+
+    ref_config, ref_sys, ref_opt = _import_systems()
+    case = dict(TRAIN_CASE)
+    if n_steps is not None:
+        case["n_steps"] = n_steps
+    R, S, NI, n_img = case["R"], case["S"], case["NI"], case["n_img"]
+    cfgs, sd0 = _train_state(case)
+    for k in ("nerf_coarse.progress", "nerf_fine.progress"):
+        sd0[k] = torch.tensor(float(start))
+    system = _build_system(ref_sys.NeRFSystem, ref_config, case)
+    missing = system.load_state_dict(sd0, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    _wire(system)
+    system.global_step = int(round(start * 2 * case["max_steps"]))
+    arrays = {f"case__{k}": torch.tensor(v) for k, v in case.items()}
+    arrays["start"] = torch.tensor(float(start))
+    arrays["state_keys"] = np.array(list(system.state_dict().keys()), dtype="U80")
+    for it in range(case["n_steps"]):
+        b = synth.ray_batch(R, n_img, 100 + it)
+        progress = float(system.nerf_coarse.progress.detach())
+        m = system.get_schedule_mult(progress)
+        seed = 5000 + it
+        for k, v in _replay_rng(seed, R, S, NI, m).items():
+            arrays[f"s{it}__{k}"] = v
+        torch.manual_seed(seed)
+        loss = system.training_step({k: v.clone() for k, v in b.items()}, it)
+        arrays[f"s{it}__progress"] = torch.tensor(progress)
+        arrays[f"s{it}__sched_mult"] = torch.tensor(float(m))
+        arrays[f"s{it}__loss"] = loss.detach()
+        for k, v in system.logged.items():
+            if k.startswith("train/") or k.startswith("lr"):
+                arrays[f"s{it}__log__{k}"] = torch.as_tensor(v).detach().float().reshape(-1)
+        arrays[f"s{it}__global_step"] = torch.tensor(system.global_step)
+        arrays[f"s{it}__progress_after"] = system.nerf_coarse.progress.detach().clone()
+        # gradients of the step as left in .grad (None = tensor not reached in this phase)
+        gnames = []
+        for k, p in system.named_parameters():
+            if p.grad is None:
+                gnames.append(k)
+            else:
+                arrays[f"s{it}__gnorm__{k}"] = p.grad.double().norm().float()
+                if p.grad.numel() <= 4096 and start > 0:
+                    arrays[f"s{it}__gfull__{k}"] = p.grad.detach().clone()
+        arrays[f"s{it}__gnone"] = np.array(gnames, dtype="U80")
+        _state_digest(f"s{it}__p", {k: v for k, v in system.state_dict().items() if "progress" not in k}, arrays)
+    _save(name, **arrays)
+
+
+def gen_tto_step():
+    """Real `NeRFSystemOptimize.training_step` / `forward` / `configure_optimizers`
+    (models/nerf_system_optmize.py:48-64,84-150), both `pose_optimize` settings, three steps each.  Its
+    `model_setup` (:253-332) needs a checkpoint file, a COLMAP scene and GT poses: the part of it that
+    matters to the step (:257-266 -- fresh embedding_fine_a over the test images as the only trained
+    module, encode_candidate off) is applied here on top of the real `NeRFSystem.model_setup`."""
+    import tempfile
+
+    from . import synth
+
+    ref_config, ref_sys, ref_opt = _import_systems()
+    case = dict(TRAIN_CASE, n_steps=3)
+    R, S, NI, n_img = case["R"], case["S"], case["NI"], case["n_img"]
+    for pose_optimize in (True, False):
+        cfgs, sd0 = _train_state(case)
+        for k in ("nerf_coarse.progress", "nerf_fine.progress"):
+            sd0[k] = torch.tensor(1.0)        # a trained checkpoint: PE fully open
+        with tempfile.TemporaryDirectory() as d:
+            system = _build_system(ref_opt.NeRFSystemOptimize, ref_config, case,
+                                   extra={"pose_optimize": pose_optimize, "out_dir": d, "optimize_num": 0,
+                                          "ckpt_path": d + "/none.ckpt"})
+        system.load_state_dict(sd0, strict=True)
+        with torch.no_grad():
+            system.embedding_fine_a = torch.nn.Embedding(n_img, system.hparams["nerf.appearance_dim"])
+            system.embedding_fine_a.weight.copy_(synth.uniform((n_img, 48), 77, -0.5, 0.5))
+            system.embeddings["fine_a"] = system.embedding_fine_a
+            system.models_to_train = [system.embedding_fine_a]
+            system.nerf_coarse.encode_candidate = False
+            system.nerf_fine.encode_candidate = False
+        _wire(system)
+        tag = "pose" if pose_optimize else "emb"
+        arrays = {f"case__{k}": torch.tensor(v) for k, v in case.items()}
+        arrays["emb_fine_a0"] = system.embedding_fine_a.weight.detach().clone()
+        before = {k: v.detach().clone() for k, v in system.state_dict().items()}
+        for it in range(case["n_steps"]):
+            b = synth.ray_batch(R, n_img, 300 + it)
+            seed = 7000 + it
+            for k, v in _replay_rng(seed, R, S, NI, 1.0, cand=False).items():
+                arrays[f"s{it}__{k}"] = v
+            torch.manual_seed(seed)
+            loss = system.training_step({k: v.clone() for k, v in b.items()}, it)
+            arrays[f"s{it}__loss"] = loss.detach()
+            arrays[f"s{it}__psnr"] = torch.as_tensor(system.logged["train/psnr"]).detach().float()
+            arrays[f"s{it}__emb_fine_a"] = system.embedding_fine_a.weight.detach().clone()
+            arrays[f"s{it}__se3_refine"] = system.se3_refine.weight.detach().clone()
+            arrays[f"s{it}__g_emb_fine_a"] = system.embedding_fine_a.weight.grad.detach().clone()
+            if pose_optimize:
+                arrays[f"s{it}__g_se3_refine"] = system.se3_refine.weight.grad.detach().clone()
+        after = system.state_dict()
+        frozen = [k for k in before if k not in ("embedding_fine_a.weight", "se3_refine.weight")]
+        assert all(torch.equal(before[k], after[k]) for k in frozen)     # networks stay frozen
+        if not pose_optimize:
+            assert torch.equal(before["se3_refine.weight"], after["se3_refine.weight"])
+        _save(f"tto_step_real_{tag}", **arrays)
+
+
 def main():
     ref_nerf, ref_rendering, ref_camera, ref_ray, ref_tnet, ref_losses = _import_reference()
     torch.set_num_threads(4)
@@ -402,6 +661,10 @@ def main():
     gen_tail(ref_tnet, ref_losses)
     gen_ray_batch()
     gen_pose_metric(ref_camera)
+    gen_train_step()
+    gen_train_step("train_step_real_p03", start=0.3, n_steps=2)
+    gen_train_step("train_step_real_p06", start=0.6, n_steps=2)
+    gen_tto_step()
 
 
 if __name__ == "__main__":

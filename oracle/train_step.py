@@ -47,7 +47,10 @@ class OracleSystem:
             o_.step()
             s_.step()
         self.step_no += 1
-        self.progress = (2 * self.step_no) / (2 * self.max_steps)
+        # the reference stores progress in an fp32 Parameter and reads it back with .item()
+        # (models/nerf_system.py:180,220-226): the schedule sees the fp32-ROUNDED value, e.g. 0.1 ->
+        # 0.100000001 > candidate_schedule[0], which already selects phase 1 with sched_mult ~ 5e-17
+        self.progress = float(torch.tensor((2 * self.step_no) / (2 * self.max_steps), dtype=torch.float32))
         return loss.detach(), res
 
 

@@ -268,7 +268,9 @@ class NeRFSystem(nn.Module):
         return keys
 
     def set_progress(self, progress: float):
-        self._progress = float(progress)
+        # the reference keeps progress in an fp32 Parameter and reads it back with .item()
+        # (models/nerf_system.py:180,220-226): the schedule sees the fp32-rounded value
+        self._progress = float(torch.tensor(float(progress), dtype=torch.float32))
         self.nerf_coarse.progress.data.fill_(self._progress)
         if self.fine:
             self.nerf_fine.progress.data.fill_(self._progress)
