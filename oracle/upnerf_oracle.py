@@ -315,7 +315,8 @@ class RenderRng:
 def render_rays(nets: dict, cfgs: dict, embeddings: dict, rays: torch.Tensor, img_idx: torch.Tensor,
                 sched_mult: float, progress: float, N_samples: int = 64, use_disp: bool = False,
                 perturb: float = 0.0, N_importance: int = 0, encode_feat: bool = True,
-                rng: RenderRng | None = None, return_aux: bool = False) -> dict:
+                rng: RenderRng | None = None, return_aux: bool = False,
+                z_fine_override: torch.Tensor | None = None) -> dict:
     """Coarse + fine rendering of a ray batch (models/rendering.py:53-314).
 
     nets/cfgs: {"nerf_coarse": ..., "nerf_fine": ...}; embeddings: {"coarse_a": (N_img,48) ...}
@@ -359,6 +360,9 @@ def render_rays(nets: dict, cfgs: dict, embeddings: dict, rays: torch.Tensor, im
         else:                                                                 # rendering.py:291-307
             new = [draw("s_weights_coarse", N_importance)]
         z_fine = torch.sort(torch.cat([z, *new], -1), -1)[0]
+        if z_fine_override is not None:       # tests: evaluate the fine pass at depths another path produced
+            assert z_fine_override.shape == z_fine.shape
+            z_fine = z_fine_override.to(z_fine.dtype)
         aux["z_fine"] = z_fine
         run("fine", z_fine)
     if return_aux:

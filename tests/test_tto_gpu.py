@@ -112,3 +112,81 @@ def test_tto_step_bf16_and_validation(cuda_dev):
     mse = ((ref["s_rgb_fine"] - vb["rgbs"]) ** 2).mean()
     assert abs(float(out["psnr"]) - float(-10 * torch.log10(mse))) <= 1e-3
     assert float(sys32.best_psnr) == float(out["psnr"])
+
+
+@pytest.mark.parametrize("tag", ["pose", "emb"])
+def test_tto_step_matches_real_reference_golden(cuda_dev, tag):
+    """The CUDA path against tests/golden/tto_step_real_*.npz, written by the REAL
+    `NeRFSystemOptimize.training_step` (models/nerf_system_optmize.py:113-150) -- not via the oracle."""
+    from pathlib import Path
+
+    import numpy as np
+
+    from oracle.make_golden import TRAIN_CASE, _train_state
+    from upnerf_b200.models.nerf_system_optmize import NeRFSystemOptimize
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / f"tto_step_real_{tag}.npz")
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    case = {k: int(g[f"case__{k}"]) for k in TRAIN_CASE}
+    R, S, NI, n_img = case["R"], case["S"], case["NI"], case["n_img"]
+    cfgs, sd0 = _train_state(case)
+    for k in ("nerf_coarse.progress", "nerf_fine.progress"):
+        sd0[k] = torch.tensor(1.0)
+    hp = {"nerf.N_samples": S, "nerf.N_importance": NI, "kernel.precision": "fp32", "pose_optimize": tag == "pose"}
+    sys_ = NeRFSystemOptimize(hp, N_images_train=n_img, N_images_test=n_img, checkpoint=None, device=cuda_dev)
+    sd0["embedding_fine_a.weight"] = g["emb_fine_a0"].clone()
+    sys_.load_state_dict(sd0)
+    for it in range(case["n_steps"]):
+        b = synth.ray_batch(R, n_img, 300 + it)
+        rng = dict(perturb_rand=g[f"s{it}__perturb_rand"], u=[g[f"s{it}__u0"]])
+        l = sys_.training_step({k: v.to(cuda_dev) for k, v in b.items()}, it, rng=rng)
+        ref = float(g[f"s{it}__loss"])
+        assert abs(float(l) - ref) <= 1e-4 * max(1.0, abs(ref)), (it, float(l), ref)
+        assert abs(float(sys_.logged["train/psnr"]) - float(g[f"s{it}__psnr"])) <= 1e-2
+        ge = sys_.group_tto.flat.grad.view(n_img, -1).cpu()
+        rg = g[f"s{it}__g_emb_fine_a"]
+        assert float((ge - rg).norm()) <= 1e-2 * float(rg.norm()), (it, float((ge - rg).norm()), float(rg.norm()))
+        if tag == "pose":
+            gp = sys_.se3_refine.weight.grad.cpu()
+            rgp = g[f"s{it}__g_se3_refine"]
+            assert float((gp - rgp).norm()) <= 1e-2 * float(rgp.norm()), it
+        own = sys_.state_dict()
+        e_ref = g[f"s{it}__emb_fine_a"]
+        upd = e_ref - g["emb_fine_a0"]
+        assert float((own["embedding_fine_a.weight"].cpu() - e_ref).norm()) <= 0.05 * float(upd.norm()), it
+        if tag == "pose":
+            upd = g[f"s{it}__se3_refine"] - sd0["se3_refine.weight"]
+            assert float((own["se3_refine.weight"].cpu() - g[f"s{it}__se3_refine"]).norm()) <= 0.05 * float(upd.norm())
+        else:
+            assert torch.equal(own["se3_refine.weight"].cpu(), g[f"s{it}__se3_refine"])
+
+
+def test_dead_pass_backward_is_skipped(cuda_dev):
+    """Outputs the loss never read reach `_RenderFn.backward` as None (set_materialize_grads(False)), so a
+    pass without any gradient launches nothing: the backward of a loss on s_rgb_fine alone plus the
+    backward of a loss on s_rgb_coarse alone launch exactly as many kernels as the backward of both."""
+    from upnerf_b200 import _lib as L
+    from upnerf_b200.models.rendering import render_rays
+    from test_render_gpu import build_modules
+    from oracle.make_golden import NET_CASES
+
+    kw, _ = NET_CASES["full"]
+    R, S, NI, n_img = 128, 16, 16, 5
+    _, _, models, _, embs = build_modules(kw, 23, 0.75, cuda_dev, n_img, emb_seed=9)
+    b = synth.ray_batch(R, n_img, 35)
+    o, d = O.get_rays(b["directions"], b["c2w"])
+    rays0 = torch.cat([o, d, b["ray_infos"]], 1).to(cuda_dev)
+    idx = b["img_idx"].to(cuda_dev)
+    counts = {}
+    for which in ("fine", "coarse", "both"):
+        rays = rays0.clone().requires_grad_(True)
+        res = render_rays(models=models, embeddings=embs, rays=rays, img_idx=idx, sched_mult=1.0, N_samples=S,
+                          perturb=0, N_importance=NI, encode_feat=True, precision="bf16")
+        loss = sum(res[f"s_rgb_{w}"].sum() for w in (("fine", "coarse") if which == "both" else (which,)))
+        torch.cuda.synchronize()
+        n0 = L.launch_count()
+        loss.backward()
+        torch.cuda.synchronize()
+        counts[which] = L.launch_count() - n0
+    assert counts["fine"] > 0 and counts["coarse"] > 0
+    assert counts["fine"] + counts["coarse"] == counts["both"], counts

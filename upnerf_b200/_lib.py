@@ -69,6 +69,13 @@ def ptr(t: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def launch_count() -> int:
+    """Kernels the library has launched so far in this process (upnerf_launch_count)."""
+    f = lib().upnerf_launch_count
+    f.restype = C.c_longlong
+    return int(f())
+
+
 def stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

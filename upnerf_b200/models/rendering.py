@@ -10,7 +10,8 @@ Extra keyword arguments (ours): `precision="bf16"|"fp32"` (default: $UPNERF_PREC
 "bf16") and `rng=dict(perturb_rand=Tensor[R,S], u=[Tensor[R,n0], Tensor[R,n1]])` to inject the
 uniforms the reference would draw for parity tests; `grad_sink=dict(coarse=, fine=,
 coarse_a=, ...)` names fp32 buffers the backward ACCUMULATES parameter / embedding gradients into
-(slices of a flat .grad buffer) instead of returning fresh tensors to autograd.
+(slices of a flat .grad buffer) instead of returning fresh tensors to autograd;
+`return_depths=dict()` is filled with the sample depths `z_coarse` [R,S] / `z_fine` [R,S+N_importance].
 """
 from __future__ import annotations
 
@@ -81,6 +82,9 @@ class _RenderFn(torch.autograd.Function):
     def forward(ctx, meta, rays, flat_c, flat_f, emb_ca, emb_fa, emb_cc, emb_fc):
         cfg, R, S, NI = meta["cfg"], rays.shape[0], meta["N_samples"], meta["N_importance"]
         dev = rays.device
+        # outputs the loss never read arrive in backward as None (not as zero tensors): a pass without
+        # any gradient is skipped by upnerf_render_bwd, unused [R,S] weight cotangents are never built
+        ctx.set_materialize_grads(False)
         a = L.RenderArgs()
         a.cfg = cfg
         a.dtype = meta["dtype"]
@@ -106,6 +110,11 @@ class _RenderFn(torch.autograd.Function):
                 setattr(io, key, t.data_ptr())
                 outs.append(t)
                 names.append(f"{key}_{which}")
+        if meta.get("depths") is not None:        # optional debug outputs: the sample depths of both passes
+            zc = torch.empty(R, S, device=dev, dtype=torch.float32)
+            zf = torch.empty(R, S + NI, device=dev, dtype=torch.float32) if NI > 0 else None
+            a.z_coarse, a.z_fine = zc.data_ptr(), L._vp(zf)
+            meta["depths"].update(z_coarse=zc, z_fine=zf)
         a.workspace_bytes = 0
         nbytes = L.render_workspace_bytes(a)
         ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
@@ -210,7 +219,8 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
                 sched_mult=m, use_disp=use_disp, perturb=perturb, keys=_phase_keys(cfg, m),
                 img_idx=img_idx.contiguous().long(), perturb_rand=as_f32(perturb_rand), u0=as_f32(u0),
                 u1=as_f32(u1), dtype=_dtype_code(kwargs.get("precision") or default_precision()),
-                n_images=0, no_grad=False, grad_sink=kwargs.get("grad_sink"))
+                n_images=0, no_grad=False, grad_sink=kwargs.get("grad_sink"),
+                depths=kwargs.get("return_depths"))
     emb = lambda k: embeddings[k].weight if k in embeddings else None
     ea_c = emb("coarse_a") if coarse.encode_appearance else None
     ec_c = emb("coarse_c") if coarse.encode_candidate else None

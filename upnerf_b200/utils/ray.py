@@ -21,6 +21,7 @@ class _GetRaysFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, directions, c2w):
         R = directions.shape[0]
+        ctx.set_materialize_grads(False)      # an unused output arrives as None, not as a zero tensor
         rays = torch.empty(R, 8, device=directions.device, dtype=torch.float32)
         L.pose_rays_fwd(None, None, c2w, directions, None, rays)
         ctx.save_for_backward(directions, c2w)
@@ -29,6 +30,8 @@ class _GetRaysFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go, gd):
         directions, c2w = ctx.saved_tensors
+        if go is None and gd is None:
+            return None, None
         R = directions.shape[0]
         d_rays = torch.zeros(R, 8, device=directions.device, dtype=torch.float32)
         if go is not None:
