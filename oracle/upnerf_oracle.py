@@ -140,13 +140,13 @@ class NerfConfig:
         return self.candidate_dim > 0
 
 
-def c2f_weights(L: int, progress: float, c2f, dtype=torch.float32) -> torch.Tensor:
+def c2f_weights(L: int, progress: float, c2f, dtype=torch.float32, device=None) -> torch.Tensor:
     """Per-band coarse-to-fine weights (models/nerf.py:137-142); ones when c2f is None."""
     if c2f is None:
-        return torch.ones(L, dtype=dtype)
+        return torch.ones(L, dtype=dtype, device=device)
     start, end = c2f
-    alpha = (torch.tensor(progress, dtype=dtype) - start) / (end - start) * L
-    k = torch.arange(L, dtype=dtype)
+    alpha = (torch.tensor(progress, dtype=dtype, device=device) - start) / (end - start) * L
+    k = torch.arange(L, dtype=dtype, device=device)
     return (1 - ((alpha - k).clamp(0, 1) * math.pi).cos()) / 2
 
 
@@ -156,9 +156,9 @@ def positional_encoding(x: torch.Tensor, L: int, progress: float = 1.0, c2f=None
     Output layout per row: [x, then for each coordinate: w_k sin(x f_k) (k<L), w_k cos(x f_k)
     (k<L)], f_k = 2^k * pi computed in fp32.
     """
-    freq = (2 ** torch.arange(L, dtype=torch.float32) * math.pi).to(x.dtype)
+    freq = (2 ** torch.arange(L, dtype=torch.float32, device=x.device) * math.pi).to(x.dtype)
     spec = x[..., None] * freq
-    w = c2f_weights(L, progress, c2f, x.dtype)
+    w = c2f_weights(L, progress, c2f, x.dtype, x.device)
     enc = torch.stack([spec.sin() * w, spec.cos() * w], -2)  # (..., 3, 2, L)
     return torch.cat([x, enc.reshape(*x.shape[:-1], -1)], -1)
 
@@ -275,7 +275,8 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n: int, det: bool = Fa
     R, nw = weights.shape
     cdf = pdf_cdf(weights, eps)
     if u is None:
-        u = torch.linspace(0, 1, n, dtype=bins.dtype).expand(R, n) if det else torch.rand(R, n, dtype=bins.dtype)
+        u = (torch.linspace(0, 1, n, dtype=bins.dtype, device=bins.device).expand(R, n) if det
+             else torch.rand(R, n, dtype=bins.dtype, device=bins.device))
     u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = (inds - 1).clamp_min(0)
@@ -291,7 +292,7 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n: int, det: bool = Fa
 def stratified_z(near: torch.Tensor, far: torch.Tensor, S: int, use_disp: bool = False,
                  perturb: float = 0.0, perturb_rand: torch.Tensor | None = None) -> torch.Tensor:
     """Coarse sample depths (models/rendering.py:231-249). near/far are (R,1)."""
-    s = torch.linspace(0, 1, S, dtype=near.dtype)
+    s = torch.linspace(0, 1, S, dtype=near.dtype, device=near.device)
     z = 1 / (1 / near * (1 - s) + 1 / far * s) if use_disp else near * (1 - s) + far * s
     z = z.expand(near.shape[0], S)
     if perturb > 0:

@@ -153,3 +153,74 @@ def pose_inv(p):
     from upnerf_b200.utils.metric import _invert
 
     return _invert(p)
+
+
+@pytest.mark.gpu
+def test_resume_from_reference_layout_checkpoint(cuda_dev, tmp_path):
+    """A checkpoint whose optimiser states are in the REFERENCE's layout (two torch.optim.Adam over ~150
+    tensors in the order of models/nerf_system.py:340-409 / utils/optim.py:7-17) resumes with its Adam
+    moments, per-tensor step counts and decayed learning rates -- not with a silently reset optimiser."""
+    import warnings
+
+    from upnerf_b200.models.nerf_system import NeRFSystem
+    from upnerf_b200.utils import ckpt as CK
+
+    hp = {"nerf.N_samples": 16, "nerf.N_importance": 16, "max_steps": 1000}
+    n_img, iters = 6, 40
+    torch.manual_seed(0)
+    sys_ = NeRFSystem(hp, N_images_train=n_img, device=cuda_dev)
+    order = [CK._reference_param_order(sys_, w) for w in (0, 1)]
+    # what the reference would have saved: per-tensor Adam states + ExponentialLR states after `iters` steps;
+    # phase-2-only tensors (candidate head) stopped earlier, `progress` never got a gradient
+    g = torch.Generator().manual_seed(4)
+    name_of = {id(p): k for k, p in sys_.named_parameters()}
+    ostates, sstates, lrs = [], [], []
+    for w, lr0, lr_end in ((0, 5e-4, 5e-5), (1, 2e-3, 1e-5)):
+        gamma = (lr_end / lr0) ** (1 / hp["max_steps"])
+        state = {}
+        for i, p in enumerate(order[w]):
+            nm = name_of[id(p)]
+            if nm.endswith("progress") or ".rgb_layer." in nm:
+                continue
+            step = 25 if ".candidate_" in nm else iters
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": torch.randn(p.shape, generator=g) * 1e-3,
+                        "exp_avg_sq": torch.rand(p.shape, generator=g) * 1e-6}
+        lr = lr0 * gamma ** iters
+        lrs.append(lr)
+        ostates.append({"state": state, "param_groups": [{"lr": lr, "initial_lr": lr0, "betas": (0.9, 0.999), "eps": 1e-8,
+                                                          "weight_decay": 0, "params": list(range(len(order[w])))}]})
+        sstates.append({"gamma": gamma, "base_lrs": [lr0], "last_epoch": iters, "_step_count": iters + 1,
+                        "_get_lr_called_within_step": False, "_last_lr": [lr]})
+    f = tmp_path / "ref.ckpt"
+    torch.save({"state_dict": {k: v.cpu() for k, v in sys_.state_dict().items()}, "global_step": 2 * iters,
+                "optimizer_states": ostates, "lr_schedulers": sstates}, f)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")          # a full restore must not warn
+        CK.load_checkpoint(sys_, str(f))
+    for w, (opt, grp) in enumerate(((sys_.optimizer, sys_.group_main), (sys_.optimizer_pose, sys_.group_pose))):
+        assert abs(opt.param_groups[0]["lr"] - lrs[w]) < 1e-12
+        st = opt.state[grp.flat]
+        for i, p in enumerate(order[w]):
+            off, n = grp.offsets[id(p)]
+            ref = ostates[w]["state"].get(i)
+            if ref is None:
+                assert float(st["exp_avg"][off:off + n].abs().max()) == 0
+                continue
+            assert torch.equal(st["exp_avg"][off:off + n].cpu(), ref["exp_avg"].reshape(-1))
+            assert torch.equal(st["exp_avg_sq"][off:off + n].cpu(), ref["exp_avg_sq"].reshape(-1))
+    assert sys_.optimizer.class_steps["always"] == iters and sys_.optimizer.class_steps["cand"] == 25
+    assert sys_.optimizer.class_steps["never"] == 0
+    # the next scheduler step continues the decay from the restored lr
+    sys_.scheduler.step()
+    gamma = (5e-5 / 5e-4) ** (1 / hp["max_steps"])
+    assert abs(sys_.optimizer.param_groups[0]["lr"] - lrs[0] * gamma) < 1e-12
+    # a checkpoint WITHOUT optimiser states: warned, lr placed on the schedule
+    f2 = tmp_path / "bare.ckpt"
+    torch.save({"state_dict": {k: v.cpu() for k, v in sys_.state_dict().items()}, "global_step": 2 * iters}, f2)
+    torch.manual_seed(1)
+    fresh = NeRFSystem(hp, N_images_train=n_img, device=cuda_dev)
+    with pytest.warns(UserWarning, match="moments restart"):
+        CK.load_checkpoint(fresh, str(f2))
+    assert abs(fresh.optimizer.param_groups[0]["lr"] - lrs[0]) < 1e-10
+    fresh.scheduler.step()
+    assert abs(fresh.optimizer.param_groups[0]["lr"] - lrs[0] * gamma) < 1e-10

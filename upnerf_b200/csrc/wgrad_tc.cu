@@ -394,7 +394,7 @@ uint64_t upnerf::wgrad_pool_floats() {
 int upnerf::wgrad_reduce(WgradBatch* batch, cudaStream_t st) {
   if (!batch || batch->list.n == 0) return UPNERF_OK;
   {
-    LaunchScope scope(kCatWgradTc, st, 0.0, 0.0);
+    LaunchScope scope(kCatWgradReduce, st, 0.0, 0.0);
     wgrad_reduce_kernel<<<batch->blocks, 128, 0, st>>>(batch->list);
     UPNERF_CHECK_LAUNCH("wgrad_reduce_kernel");
   }

@@ -71,7 +71,13 @@ def fused_tail(results, batch, depth_scale, sched_mult, *, depth_mult, alpha_reg
         keep.append(t)
         return t.data_ptr()
 
-    a.img_idx = batch["img_idx"].data_ptr()
+    idx = batch["img_idx"]
+    if not idx.is_cuda:
+        raise L.UpnerfError("fused_tail: img_idx must be a CUDA tensor")
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        idx = idx.contiguous().long()            # tail.cu reads int64 indices
+    keep.append(idx)
+    a.img_idx = idx.data_ptr()
     a.inv_depths, a.rgbs, a.feats = f32(batch["inv_depths"]), f32(rgbs), f32(batch["feats"])
     a.depth_scale = f32(depth_scale)
     if depth_scale.grad is not None:

@@ -79,6 +79,18 @@ class FlatGroup:
     def zero_grad(self):
         self.flat.grad.zero_()
 
+    def check(self):
+        """Every parameter (and its .grad) must still be the view of the flat buffers it was made: a later
+        `module.to()`, `.float()`, `zero_grad(set_to_none=True)` or `load_state_dict(assign=True)` on a
+        sub-module silently re-homes tensors, and the fused optimiser would then update stale memory."""
+        es = self.flat.element_size()
+        base, gbase = self.flat.data_ptr(), self.flat.grad.data_ptr()
+        for p in self.params:
+            off, _ = self.offsets[id(p)]
+            if p.data_ptr() != base + off * es or p.grad is None or p.grad.data_ptr() != gbase + off * es:
+                raise RuntimeError("a parameter of NeRFSystem no longer aliases its flat buffer (was a sub-module "
+                                   "moved, cast, or its gradients set to None?); rebuild the system instead")
+
     def segments(self):
         """[(end_offset, class_key)] runs covering the buffer (the FlatAdam segment table)."""
         return [(self.offsets[id(p)][0] + self.offsets[id(p)][1], k) for p, k in zip(self.params, self.keys)]
@@ -144,6 +156,12 @@ class NeRFSystem(nn.Module):
         self._progress = 0.0
         self._tail_ws = None
         self._side_stream = None
+        self._steps_seen = 0
+        if self.hparams["nerf.feat_dim"] <= 0 and self.hparams["nerf.candidate_dim"] > 0:
+            raise NotImplementedError(
+                "upnerf_b200: encode_feat=False (nerf.feat_dim <= 0) together with a candidate head -- the "
+                "reference's c_rgb_* / l_c_rgb_* path (models/rendering.py:134-150) -- is not implemented; "
+                "use nerf.feat_dim > 0, or nerf.candidate_dim = 0 (INTEGRATION.md section 3)")
         self.white_back = False
         if N_images_train is not None:
             self.model_setup(N_images_train)
@@ -179,6 +197,7 @@ class NeRFSystem(nn.Module):
         nn.init.zeros_(self.se3_refine.weight)
         self.depth_scale = nn.Embedding(N_images, 2)
         nn.init.zeros_(self.depth_scale.weight)
+        self.group_main = None
         self.to(self._device)
         # flat buffers: group 0 = reference optimizer 0 (networks + embeddings), group 1 = pose
         main, keys = [], []
@@ -200,6 +219,19 @@ class NeRFSystem(nn.Module):
             self._grad_sinks[which] = self.group_main.grad_of(m.parameters())
         for ename, e in self.embeddings.items():
             self._grad_sinks[ename] = self.group_main.grad_of([e.weight])
+
+    def _apply(self, fn, recurse=True):
+        # nn.Module.to()/.float()/.cuda() replace parameter storage; once the flat buffers exist that would
+        # detach every view from them (FlatAdam and the gradient sinks would update stale memory)
+        if getattr(self, "group_main", None) is not None:
+            raise RuntimeError("NeRFSystem: parameters are views of flat buffers; construct it with device=... "
+                               "instead of moving or casting it afterwards")
+        return super()._apply(fn, recurse)
+
+    def zero_grad(self, set_to_none=False):
+        """Gradients live in the flat buffers: they are zeroed in place, never set to None."""
+        self.group_main.zero_grad()
+        self.group_pose.zero_grad()
 
     def load_state_dict(self, sd, strict=True):
         # parameters are views of the flat buffers: copy in place so the views stay valid
@@ -328,6 +360,17 @@ class NeRFSystem(nn.Module):
         """models/nerf_system.py:150-229."""
         hp = self.hparams
         img_idx = batch["img_idx"]
+        if img_idx.dtype != torch.int64 or not img_idx.is_contiguous():
+            img_idx = img_idx.contiguous().long()       # the kernels read int64 indices
+            batch = dict(batch, img_idx=img_idx)
+        if self._steps_seen % 256 == 0:
+            # cheap invariants, checked on the first step and then rarely (one host sync): indices in range
+            # (nn.Embedding would raise; the kernels index raw tables) and the flat-buffer aliasing
+            if img_idx.numel() and not (0 <= int(img_idx.min()) and int(img_idx.max()) < self.N_images):
+                raise IndexError(f"img_idx out of range [0, {self.N_images})")
+            self.group_main.check()
+            self.group_pose.check()
+        self._steps_seen += 1
         if hp["pose.optimize"]:
             rays = ray_utils.refine_rays(self.se3_refine.weight, img_idx, batch["c2w"], batch["directions"],
                                          batch["ray_infos"])
@@ -373,9 +416,10 @@ class NeRFSystem(nn.Module):
                     psnr_ = -10 * torch.log10(((results[f"s_rgb_{typ}"] - batch["rgbs"]) ** 2).mean())
                 else:
                     psnr_ = torch.zeros(1)
-        allreduce_mean_(self.group_main.flat.grad)
-        if hp["pose.optimize"]:
-            allreduce_mean_(self.group_pose.flat.grad)
+        if not hp.get("kernel.skip_allreduce", False):      # (bench.py measures the step without it)
+            allreduce_mean_(self.group_main.flat.grad)
+            if hp["pose.optimize"]:
+                allreduce_mean_(self.group_pose.flat.grad)
         live = {"always": True, "never": False, "rgb": sched_mult > 0 or hp["nerf.feat_dim"] <= 0,
                 "cand": sched_mult < 1}
         for opt, sch in zip(self._optimizers, self._schedulers):

@@ -53,10 +53,66 @@ def save_checkpoint(system, path):
     return ckpt
 
 
+def _reference_param_order(system, which):
+    """Parameters in the order the REFERENCE hands them to optimiser `which` (models/nerf_system.py:340-409,
+    utils/optim.py:7-17): 0 = the embedding tables (coarse_a, fine_a, coarse_c, fine_c), then nerf_coarse,
+    nerf_fine, transient_net; 1 = depth_scale, se3_refine."""
+    if which == 1:
+        return [system.depth_scale.weight, system.se3_refine.weight]
+    out = []
+    for tag in ("a", "c"):
+        for lvl in ("coarse", "fine"):
+            e = system.embeddings.get(f"{lvl}_{tag}")
+            if e is not None:
+                out += list(e.parameters())
+    for m in system.models.values():
+        out += list(m.parameters())
+    return out
+
+
+def _load_reference_optimizer(system, which, opt, state):
+    """Map a torch.optim.Adam state_dict in the reference's per-tensor layout onto a FlatAdam: exp_avg /
+    exp_avg_sq go into the flat moment buffers at each tensor's offset, the per-tensor step counts become
+    the per-class counters (tensors of one liveness class share their history), lr comes from param_groups."""
+    group = system.group_main if which == 0 else system.group_pose
+    params = _reference_param_order(system, which)
+    ids = state["param_groups"][0]["params"]
+    if len(ids) != len(params):
+        raise ValueError(f"optimizer {which}: {len(ids)} tensors in the checkpoint, {len(params)} here")
+    flat = opt.param_groups[0]["params"][0]
+    st = opt.state[flat]
+    st["exp_avg"].zero_()
+    st["exp_avg_sq"].zero_()
+    key_of = {id(p): k for p, k in zip(group.params, group.keys)}
+    steps = {k: 0 for k in opt.class_steps}
+    for pid, p in zip(ids, params):
+        ts = state["state"].get(pid)
+        if ts is None:          # never received a gradient
+            continue
+        off, n = group.offsets[id(p)]
+        if ts["exp_avg"].numel() != n:
+            raise ValueError(f"optimizer {which}: tensor {pid} has {ts['exp_avg'].numel()} elements, expected {n}")
+        st["exp_avg"][off:off + n].copy_(ts["exp_avg"].reshape(-1))
+        st["exp_avg_sq"][off:off + n].copy_(ts["exp_avg_sq"].reshape(-1))
+        k = key_of[id(p)]
+        steps[k] = max(steps[k], int(ts["step"]))
+    opt.class_steps.update(steps)
+    g_src, g_dst = state["param_groups"][0], opt.param_groups[0]
+    g_dst["lr"] = float(g_src["lr"])
+    if "initial_lr" in g_src:
+        g_dst["initial_lr"] = float(g_src["initial_lr"])
+
+
 def load_checkpoint(system, path, strict=True, resume=True):
     """Load a Lightning-format checkpoint (ours or the reference's) into `system`; with `resume`, also the
-    step counter, the schedule progress it implies (models/nerf_system.py:222-228) and, when the file
-    has them in this package's flat-buffer layout, the optimiser / scheduler states."""
+    step counter, the schedule progress it implies (models/nerf_system.py:222-228) and the optimiser /
+    scheduler states -- in this package's flat layout, or mapped from the reference's per-tensor Adam
+    state.  If an optimiser state cannot be restored at all, a warning is issued and the learning rate
+    is set to where the ExponentialLR schedule stands at the restored step (moments restart from zero)."""
+    import warnings
+
+    from ..optim import FlatAdam
+
     ckpt = torch.load(path, map_location=torch.device("cpu"), weights_only=False)
     sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
     system.load_state_dict(sd, strict=strict)
@@ -64,16 +120,33 @@ def load_checkpoint(system, path, strict=True, resume=True):
         system.global_step = int(ckpt["global_step"])
         if system.hparams.get("pose.optimize", False):
             system.set_progress(system.global_step / (system.hparams["max_steps"] * 2))
-        for key, objs in (("optimizer_states", getattr(system, "_optimizers", [])),
-                          ("lr_schedulers", getattr(system, "_schedulers", []))):
-            states = ckpt.get(key) or []
-            if len(states) == len(objs):
-                for o, st in zip(objs, states):
-                    try:
-                        o.load_state_dict(st)
-                    except (ValueError, KeyError, RuntimeError):
-                        # a reference checkpoint: per-tensor optimiser state, not the flat layout
-                        pass
+        opts, schs = getattr(system, "_optimizers", []), getattr(system, "_schedulers", [])
+        ostates, sstates = ckpt.get("optimizer_states") or [], ckpt.get("lr_schedulers") or []
+        iters = system.global_step // max(1, len(opts))
+        for i, o in enumerate(opts):
+            restored = False
+            if len(ostates) == len(opts):
+                try:
+                    if isinstance(o, FlatAdam) and "class_steps" not in ostates[i]:
+                        _load_reference_optimizer(system, i, o, ostates[i])
+                    else:
+                        o.load_state_dict(ostates[i])
+                    restored = True
+                except (ValueError, KeyError, RuntimeError) as e:
+                    warnings.warn(f"load_checkpoint: optimizer {i} state not restored ({e}); Adam moments restart from zero")
+            else:
+                warnings.warn(f"load_checkpoint: no state for optimizer {i} in the checkpoint; Adam moments restart from zero")
+            if i < len(schs):
+                if len(sstates) == len(schs):
+                    schs[i].load_state_dict(sstates[i])
+                else:
+                    schs[i].last_epoch = iters
+                if not restored or len(sstates) != len(schs):
+                    # put the learning rate where the schedule stands: lr0 * gamma ** iterations
+                    g = o.param_groups[0]
+                    lr0 = g.get("initial_lr", g["lr"])
+                    g["lr"] = lr0 * schs[i].gamma ** iters
+                schs[i]._last_lr = [g["lr"] for g in o.param_groups]
     return ckpt
 
 
