@@ -508,13 +508,14 @@ def run_render(args):
     c2w = torch.eye(3, 4, device=dev)
     idx = torch.zeros(R, dtype=torch.long, device=dev)
     feats = torch.zeros(R, 384, device=dev)
-    nf = torch.tensor([[0.1, 5.0]], device=dev).expand(R, 2)
+    nf_row = torch.tensor([[0.1, 5.0]], device=dev)
     out_host = torch.empty(R, 3).pin_memory()
 
     def render(dirs):
+        n = dirs.shape[0]
         o, d = get_rays(dirs, c2w)
-        rays = torch.cat([o, d, nf], 1)
-        return system(rays, feats, idx, 1.0, train=False)["rgb_fine"]
+        rays = torch.cat([o, d, nf_row.expand(n, 2)], 1)
+        return system(rays, feats[:n], idx[:n], 1.0, train=False)["rgb_fine"]
 
     dirs_dev = dirs_host.to(dev)
     with torch.no_grad():

@@ -163,8 +163,46 @@ def positional_encoding(x: torch.Tensor, L: int, progress: float = 1.0, c2f=None
     return torch.cat([x, enc.reshape(*x.shape[:-1], -1)], -1)
 
 
+class _RoundOperand(torch.autograd.Function):
+    """x -> x rounded to `dtype` (value kept in x's own dtype); the incoming gradient is rounded the same
+    way.  Emulates a path that STORES activations / their gradients in a narrow type and accumulates wide."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).to(g.dtype), None
+
+
+# None: exact arithmetic in the tensors' own dtype (the reference).  torch.bfloat16: every dense layer of
+# NeRF.forward sees its input activations and its weight matrix rounded to bf16 and accumulates in the
+# tensors' dtype -- "the reference's arithmetic with bf16 operands", the floor of ANY bf16 tensor-core
+# implementation.  Used by tests/test_baseline_size_gpu.py to show where the CUDA path's bf16 gradient
+# error comes from (ReLU sign flips of near-zero pre-activations), not by the parity oracle itself.
+OPERAND_ROUNDING = None
+
+
+class operand_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global OPERAND_ROUNDING
+        self.prev, OPERAND_ROUNDING = OPERAND_ROUNDING, self.dtype
+
+    def __exit__(self, *exc):
+        global OPERAND_ROUNDING
+        OPERAND_ROUNDING = self.prev
+
+
 def _linear(p: dict, name: str, x: torch.Tensor) -> torch.Tensor:
-    return F.linear(x, p[name + ".weight"], p[name + ".bias"])
+    w = p[name + ".weight"]
+    if OPERAND_ROUNDING is not None and w.shape[0] > 3:        # the N = 1 / 3 heads stay fp32 row-dots
+        x, w = _RoundOperand.apply(x, OPERAND_ROUNDING), _RoundOperand.apply(w, OPERAND_ROUNDING)
+    return F.linear(x, w, p[name + ".bias"])
 
 
 def nerf_forward(p: dict, cfg: NerfConfig, xyz: torch.Tensor, dirs: torch.Tensor,

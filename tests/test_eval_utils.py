@@ -162,7 +162,7 @@ def test_resume_from_reference_layout_checkpoint(cuda_dev, tmp_path):
     moments, per-tensor step counts and decayed learning rates -- not with a silently reset optimiser."""
     import warnings
 
-    from upnerf_b200.models.nerf_system import NeRFSystem
+    from upnerf_b200.models.nerf_system import NeRFSystem, adam_class
     from upnerf_b200.utils import ckpt as CK
 
     hp = {"nerf.N_samples": 16, "nerf.N_importance": 16, "max_steps": 1000}
@@ -180,9 +180,9 @@ def test_resume_from_reference_layout_checkpoint(cuda_dev, tmp_path):
         state = {}
         for i, p in enumerate(order[w]):
             nm = name_of[id(p)]
-            if nm.endswith("progress") or ".rgb_layer." in nm:
+            if adam_class(nm) == "never":
                 continue
-            step = 25 if ".candidate_" in nm else iters
+            step = 25 if adam_class(nm) == "cand" else iters
             state[i] = {"step": torch.tensor(float(step)), "exp_avg": torch.randn(p.shape, generator=g) * 1e-3,
                         "exp_avg_sq": torch.rand(p.shape, generator=g) * 1e-6}
         lr = lr0 * gamma ** iters
@@ -209,7 +209,7 @@ def test_resume_from_reference_layout_checkpoint(cuda_dev, tmp_path):
             assert torch.equal(st["exp_avg"][off:off + n].cpu(), ref["exp_avg"].reshape(-1))
             assert torch.equal(st["exp_avg_sq"][off:off + n].cpu(), ref["exp_avg_sq"].reshape(-1))
     assert sys_.optimizer.class_steps["always"] == iters and sys_.optimizer.class_steps["cand"] == 25
-    assert sys_.optimizer.class_steps["never"] == 0
+    assert sys_.optimizer.class_steps["never"] == 0 and sys_.optimizer_pose.class_steps["cand"] == 25
     # the next scheduler step continues the decay from the restored lr
     sys_.scheduler.step()
     gamma = (5e-5 / 5e-4) ** (1 / hp["max_steps"])
