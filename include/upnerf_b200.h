@@ -491,6 +491,37 @@ typedef struct upnerf_ray_batch_args {
 } upnerf_ray_batch_args;
 int upnerf_ray_batch_gather(const upnerf_ray_batch_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * TransientNet on the tensor cores.
+ * Replaces TransientNet.forward (models/transient_net.py:27-38) and its autograd backward:
+ *   h = feat_encoder(feats) (4 x Linear 256 + ReLU); t = ReLU(t_encoder([final_encoder(h) | embedding_t[img_idx]]));
+ *   alpha = sigmoid(alpha_layer(h)); rgb = sigmoid(rgb_layer(t)); beta = softplus(beta_layer(t)) * alpha + beta_min.
+ * bf16 operands on tcgen05 with fp32 accumulation for the six dense layers (upnerf_gemm_bf16 / the
+ * weight-gradient kernel), fp32 row-dots for the N <= 3 heads.
+ *   params[i]   fp32 tensors in state_dict order (:9-25): embedding_t.weight [n_images,128],
+ *               feat_encoder.{0,2,4,6}.{weight,bias}, final_encoder.{weight,bias}, t_encoder.0.{weight,bias},
+ *               alpha_layer.0.{weight,bias}, beta_layer.0.{weight,bias}, rgb_layer.0.{weight,bias}
+ *   d_params[i] gradients, ACCUMULATED (fp32); a NULL entry skips that tensor
+ *   alpha [R], beta [R], rgb [R,3] outputs; g_alpha / g_beta / g_rgb their upstream gradients (NULL = zero)
+ *   workspace   >= upnerf_tnet_workspace_bytes(); upnerf_tnet_bwd reads what upnerf_tnet_fwd left in it */
+#define UPNERF_TNET_PARAMS 19
+typedef struct upnerf_tnet_args {
+  int64_t n_rays;
+  int n_images, feat_dim, hidden, transient_dim;
+  float beta_min;
+  const float* feats;          /* [R, feat_dim] */
+  const int64_t* img_idx;      /* [R] */
+  const float* params[UPNERF_TNET_PARAMS];
+  float* d_params[UPNERF_TNET_PARAMS];
+  float *alpha, *beta, *rgb;
+  const float *g_alpha, *g_beta, *g_rgb;
+  void* workspace;
+  uint64_t workspace_bytes;
+} upnerf_tnet_args;
+uint64_t upnerf_tnet_workspace_bytes(const upnerf_tnet_args* a);
+int upnerf_tnet_fwd(const upnerf_tnet_args* a, void* stream);
+int upnerf_tnet_bwd(const upnerf_tnet_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -214,6 +214,35 @@ class TailArgs(C.Structure):
                 + [("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)])
 
 
+TNET_PARAMS = 19
+
+
+class TnetArgs(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("n_images", C.c_int), ("feat_dim", C.c_int), ("hidden", C.c_int),
+                ("transient_dim", C.c_int), ("beta_min", C.c_float), ("feats", C.c_void_p), ("img_idx", C.c_void_p),
+                ("params", C.c_void_p * TNET_PARAMS), ("d_params", C.c_void_p * TNET_PARAMS),
+                ("alpha", C.c_void_p), ("beta", C.c_void_p), ("rgb", C.c_void_p),
+                ("g_alpha", C.c_void_p), ("g_beta", C.c_void_p), ("g_rgb", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+def tnet_workspace_bytes(a: TnetArgs) -> int:
+    f = lib().upnerf_tnet_workspace_bytes
+    f.restype = C.c_uint64
+    n = int(f(C.byref(a)))
+    if n == 0:
+        raise UpnerfError("tnet: " + lib().upnerf_last_error().decode("utf-8", "replace"))
+    return n
+
+
+def tnet_fwd(a: TnetArgs) -> None:
+    check(lib().upnerf_tnet_fwd(C.byref(a), stream_ptr()), "upnerf_tnet_fwd")
+
+
+def tnet_bwd(a: TnetArgs) -> None:
+    check(lib().upnerf_tnet_bwd(C.byref(a), stream_ptr()), "upnerf_tnet_bwd")
+
+
 def tail_workspace_bytes() -> int:
     f = lib().upnerf_tail_workspace_bytes
     f.restype = C.c_uint64

@@ -193,6 +193,10 @@ class NeRFSystem(nn.Module):
         self.transient_net = TransientNet(N_images=N_images, beta_min=hp["t_net.beta_min"],
                                           trasient_dim=hp["t_net.transient_dim"], feat_dim=hp["t_net.feat_dim"])
         self.models["transient_network"] = self.transient_net
+        # bf16 mode: TransientNet forward/backward on the tensor-core path, gradients accumulated straight into
+        # the flat gradient buffer (its parameters' .grad are views of it)
+        self.transient_net.precision = "bf16" if hp["kernel.precision"] in ("bf16", "bfloat16") else "fp32"
+        self.transient_net.grad_sink = True
         self.se3_refine = nn.Embedding(N_images, 6)
         nn.init.zeros_(self.se3_refine.weight)
         self.depth_scale = nn.Embedding(N_images, 2)
