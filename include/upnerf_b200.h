@@ -385,6 +385,10 @@ int64_t upnerf_nerf_param_count(const upnerf_net_config* cfg);
 uint64_t upnerf_render_workspace_bytes(const upnerf_render_args* a);
 int upnerf_render_fwd(const upnerf_render_args* a, void* stream);
 int upnerf_render_bwd(const upnerf_render_args* a, void* stream);
+/* The same backward one network pass at a time: passes bit 0 = fine, bit 1 = coarse (3 = upnerf_render_bwd).
+ * Every gradient of the passes run is final on `stream` when the call returns, so a data-parallel caller can
+ * start the all-reduce of the fine network's gradients while the coarse backward runs (train.py:72). */
+int upnerf_render_bwd_passes(const upnerf_render_args* a, int passes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (f2) Per-ray tail of the train step in ONE launch.

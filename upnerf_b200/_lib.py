@@ -371,6 +371,11 @@ def render_fwd(args: RenderArgs) -> None:
     check(lib().upnerf_render_fwd(C.byref(args), stream_ptr()), "upnerf_render_fwd")
 
 
+def render_bwd_passes(args: RenderArgs, passes: int) -> None:
+    """passes: bit 0 = fine network, bit 1 = coarse network."""
+    check(lib().upnerf_render_bwd_passes(C.byref(args), C.c_int(passes), stream_ptr()), "upnerf_render_bwd_passes")
+
+
 def render_bwd(args: RenderArgs) -> None:
     check(lib().upnerf_render_bwd(C.byref(args), stream_ptr()), "upnerf_render_bwd")
 

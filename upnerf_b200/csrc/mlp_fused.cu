@@ -567,13 +567,13 @@ constexpr int kOffBias2 = kOffW2 + kStages * kStageBytes;
 constexpr int kOffHeadW2 = kOffBias2 + kNL * 256 * 4;
 constexpr int kOffHead2 = kOffHeadW2 + 256 * 4;
 constexpr int kOffBar2 = kOffHead2 + 4 * kTileM * 4;
-// wfull[3] wempty[3] pefull[2] peempty[2] act[2][4] tfull[2] tempty[2]
-constexpr int kNumBars2 = 2 * kStages + 4 + 8 + 4;
+// wfull[3] wempty[3] pefull[2] peempty[2] act[2][4] tfull[2] tempty[2] st[2][4] stfree[2][4]
+constexpr int kNumBars2 = 2 * kStages + 4 + 8 + 4 + 16;
 constexpr int kOffTmem2 = kOffBar2 + kNumBars2 * 8;
 constexpr int kSmemBytes2 = kOffTmem2 + 16 + 1024;
 static_assert(kSmemBytes2 <= 232448, "shared memory budget exceeded");
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsF, 1)
 mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -592,6 +592,8 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
   uint64_t* bar_act = bar_peempty + 2;      // [slot * 4 + box], on the leader: 8 warps of a set x 2 CTAs
   uint64_t* bar_tfull = bar_act + 8;        // [slot] accumulator complete (commit, multicast to both CTAs)
   uint64_t* bar_tempty = bar_tfull + 2;     // [slot] accumulator drained, on the leader: 16 warps x 2 CTAs
+  uint64_t* bar_st = bar_tempty + 2;        // [slot * 4 + box] lsu_store == 2: box written (8 warps of its set) -> copy-out warps
+  uint64_t* bar_stfree = bar_st + 8;        // [slot * 4 + box] box copied out (kCopyWarps arrivals) -> may be overwritten
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem2);
 
   const int warp = threadIdx.x >> 5;
@@ -618,10 +620,14 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
       mbar_init(&bar_tempty[i], 32);
     }
     for (int i = 0; i < 8; ++i) mbar_init(&bar_act[i], 16);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&bar_st[i], 8);
+      mbar_init(&bar_stfree[i], kCopyWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<512>(tmem_holder);
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 18) {
     const int t = threadIdx.x - 64;
     for (int i = t; i < kNL * 256; i += kEpiThreads) {
       const float* b = args.bias[i >> 8];
@@ -740,6 +746,48 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
         }
       }
     }
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------ copy-out warps (lsu_store == 2), see the single-tile kernel
+    if (args.lsu_store == 2) {
+      const int cw = warp - 18;
+      constexpr int kRowsPer = kTileM / kCopyWarps;           // 64
+      const int r0 = cw * kRowsPer + (lane >> 3);
+      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
+      const uint32_t so_even = r0 * 128 + x0, so_odd = r0 * 128 + (x0 ^ 64u);
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        for (int l = 0; l < kNL; ++l) {
+          if (!args.layer[l].store) continue;
+          const int64_t ldo = args.ld_out[l];
+          for (int slot = 0; slot < 2; ++slot) {
+            const int tile = (unit * 2 + slot) * 2 + cta_rank;
+            const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;
+            __nv_bfloat16* o0 = args.out[l] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
+            for (int b = 0; b < 4; ++b) {
+              mbar_wait(&bar_st[slot * 4 + b], ph);
+              const uint32_t sbox = smem_u32(sAct) + slot * kActBytes + b * kBoxBytes;
+              __nv_bfloat16* ob = o0 + b * 64;
+#pragma unroll
+              for (int h = 0; h < kRowsPer / 32; ++h) {
+                float4 vv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  vv[i] = lds128(sbox + ((i & 1) ? so_odd : so_even) + (h * 8 + i) * 512);
+                if (h == kRowsPer / 32 - 1) {
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&bar_stfree[slot * 4 + b]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (r0 + (h * 8 + i) * 4 < rows_left)
+                    __stcs(reinterpret_cast<float4*>(ob + static_cast<int64_t>((h * 8 + i) * 4) * ldo), vv[i]);
+              }
+            }
+          }
+          ph ^= 1;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue warps (as in the single-tile kernel)
     const int ew = warp - 2;
@@ -757,6 +805,7 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
     const uint32_t act_bar0 = mapa_u32(smem_u32(&bar_act[0]), 0);
     const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
     uint32_t gs = 0;
+    uint32_t nst = 0;   // lsu_store == 2: stored layers so far (= releases seen per (slot, box))
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       for (int l = 0; l < kNL; ++l, ++gs) {
         const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
@@ -778,6 +827,8 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
           for (int q = 0; q < 4; ++q) {
             const int box = set + (q & 2);
             const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+            // copy-out warps: the previous contents of this box must have been read out before my first write
+            if (args.lsu_store == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[slot * 4 + box], (nst - 1) & 1);
             tmem_ld_wait_dep(r[q & 1]);
             if (q < 3) {
               const int nbox = set + ((q + 1) & 2);
@@ -819,25 +870,26 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
             sts128(box_row + ((s0 ^ swz) << 4), o[0]);
             sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
             if (want_mask) {
-              const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
+              // bit e = [column e > 0]: v >= +0 after the ReLU, so the sign of the negated bit pattern is the predicate
               uint32_t m16 = 0;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                m16 |= ((ow[e] & 0xFFFFu) ? 1u : 0u) << (2 * e);
-                m16 |= ((ow[e] >> 16) ? 1u : 0u) << (2 * e + 1);
-              }
+              for (int e = 15; e >= 0; --e)
+                m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
               mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
             }
             if (q & 1) {
-              if (want_mask)
-                args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
               fence_proxy_async_smem();
               if (feeds) {
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane0) mbar_arrive_cluster(act_bar0 + (slot * 4 + box) * 8);
               }
-              if (store) {
+              if (want_mask)
+                args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
+              if (store && args.lsu_store == 2) {
+                __syncwarp();
+                if (lane0) mbar_arrive(&bar_st[slot * 4 + box]);   // the copy-out warps take it from here
+              } else if (store) {
                 if (leader) tma_store_wait_read<0>();
                 named_bar_sync(set_bar, kSetThreads);
                 if (leader) {
@@ -856,6 +908,7 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
             named_bar_sync(4, kEpiThreads);   // sHead is rewritten by the other slot right after
           }
         }
+        if (store) ++nst;
       }
     }
     if (leader) tma_store_wait_all<0>();
@@ -1316,7 +1369,7 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsF);
     cfg.dynamicSmemBytes = dual::kSmemBytes2;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute attr[1];

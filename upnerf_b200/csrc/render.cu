@@ -960,7 +960,9 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   return join_side(c);
 }
 
-int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
+// passes: bit 0 = the fine network's backward, bit 1 = the coarse network's.  Each call joins the side
+// stream before it returns, so every gradient of the passes it ran is final on `stream` afterwards.
+int upnerf_render_bwd_passes(const upnerf_render_args* a, int passes, void* stream) {
   using namespace upnerf;
   UPNERF_TRY(check_common(*a));
   Plan pl;
@@ -981,9 +983,12 @@ int upnerf_render_bwd(const upnerf_render_args* a, void* stream) {
     return io.g_c_weights || io.g_s_weights || io.g_c_depth || io.g_s_depth || io.g_t_weight || io.g_feat ||
            io.g_s_rgb;
   };
-  if (a->n_importance > 0 && live(a->fine)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch, 0));
-  if (live(a->coarse)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch, 1));
+  if ((passes & 1) && a->n_importance > 0 && live(a->fine))
+    UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->fine, pl.fine, pl.scratch, 0));
+  if ((passes & 2) && live(a->coarse)) UPNERF_TRY(pass_bwd(c, *a, pl.L, ph, a->coarse, pl.coarse, pl.scratch, 1));
   return join_side(c);
 }
+
+int upnerf_render_bwd(const upnerf_render_args* a, void* stream) { return upnerf_render_bwd_passes(a, 3, stream); }
 
 }  // extern "C"

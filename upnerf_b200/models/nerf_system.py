@@ -59,12 +59,17 @@ def default_hparams() -> dict:
 class FlatGroup:
     """Parameters re-homed as views of one flat fp32 buffer, gradients likewise."""
 
-    def __init__(self, params, device, keys=None):
+    def __init__(self, params, device, keys=None, grad_storage=None):
+        """`grad_storage`: an fp32 buffer of the right size to use as the flat gradient (so that several
+        groups can share ONE allocation and be all-reduced with one collective)."""
         self.params = list(params)
         self.keys = list(keys) if keys is not None else ["always"] * len(self.params)
         n = sum(p.numel() for p in self.params)
         self.flat = nn.Parameter(torch.empty(n, device=device, dtype=torch.float32))
-        self.flat.grad = torch.zeros(n, device=device, dtype=torch.float32)
+        if grad_storage is None:
+            grad_storage = torch.zeros(n, device=device, dtype=torch.float32)
+        assert grad_storage.numel() == n and grad_storage.dtype == torch.float32 and grad_storage.is_contiguous()
+        self.flat.grad = grad_storage
         off = 0
         self.offsets = {}
         with torch.no_grad():
@@ -204,8 +209,13 @@ class NeRFSystem(nn.Module):
         self.group_main = None
         self.to(self._device)
         # flat buffers: group 0 = reference optimizer 0 (networks + embeddings), group 1 = pose
+        # Layout [nerf_fine | nerf_coarse | transient_net | embeddings] + [depth_scale | se3_refine], gradients of
+        # both groups in ONE allocation: the fine network's slice is final first in backward (its all-reduce
+        # then runs under the coarse pass), everything else goes out as one more collective.
         main, keys = [], []
-        for mname, m in self.models.items():
+        order = (["nerf_fine"] if self.fine else []) + ["nerf_coarse", "transient_network"]
+        for mname in order:
+            m = self.models[mname]
             attr = {"nerf_coarse": "nerf_coarse", "nerf_fine": "nerf_fine", "transient_network": "transient_net"}[mname]
             for pname, p in m.named_parameters():
                 main.append(p)
@@ -213,9 +223,15 @@ class NeRFSystem(nn.Module):
         for ename, e in self.embeddings.items():
             main += list(e.parameters())
             keys.append(adam_class(f"embedding_{ename}.weight"))
-        self.group_main = FlatGroup(main, self._device, keys)
+        n_main = sum(p.numel() for p in main)
+        n_pose = self.depth_scale.weight.numel() + self.se3_refine.weight.numel()
+        self._grad_all = torch.zeros(n_main + n_pose, device=self._device, dtype=torch.float32)
+        self.group_main = FlatGroup(main, self._device, keys, grad_storage=self._grad_all[:n_main])
         self.group_pose = FlatGroup([self.depth_scale.weight, self.se3_refine.weight], self._device,
-                                    [adam_class("depth_scale.weight"), adam_class("se3_refine.weight")])
+                                    [adam_class("depth_scale.weight"), adam_class("se3_refine.weight")],
+                                    grad_storage=self._grad_all[n_main:])
+        self._n_fine = sum(p.numel() for p in self.nerf_fine.parameters()) if self.fine else 0
+        self._pending_reduce = None
         # the render backward accumulates straight into these slices of the flat gradient buffer
         self._grad_sinks = {}
         for which, m in (("coarse", self.nerf_coarse), *((("fine", self.nerf_fine),) if self.fine else ())):
@@ -234,8 +250,32 @@ class NeRFSystem(nn.Module):
 
     def zero_grad(self, set_to_none=False):
         """Gradients live in the flat buffers: they are zeroed in place, never set to None."""
-        self.group_main.zero_grad()
-        self.group_pose.zero_grad()
+        self._grad_all.zero_()
+
+    # ------------------------------------------------------------------ data-parallel gradient mean
+    def _ddp_active(self):
+        return (not self.hparams.get("kernel.skip_allreduce", False) and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1)
+
+    def _reduce_fine_async(self):
+        """Called between the fine and the coarse backward (`render_rays(after_fine_bwd=...)`): the fine
+        network's gradient slice is final, its mean over ranks starts now on NCCL's stream."""
+        if self._n_fine and self._grad_all.is_cuda:
+            self._pending_reduce = dist.all_reduce(self._grad_all[:self._n_fine], op=dist.ReduceOp.AVG, async_op=True)
+
+    def _reduce_gradients(self):
+        """DDP semantics (train.py:72): mean over ranks of every gradient -- the rest of the single gradient
+        buffer in one collective, then wait for the fine slice started earlier."""
+        if not self._ddp_active():
+            return
+        lo = self._n_fine if self._pending_reduce is not None else 0
+        if not self.hparams["pose.optimize"]:
+            allreduce_mean_(self._grad_all[lo:self.group_main.flat.numel()])
+        else:
+            allreduce_mean_(self._grad_all[lo:])
+        if self._pending_reduce is not None:
+            self._pending_reduce.wait()
+            self._pending_reduce = None
 
     def load_state_dict(self, sd, strict=True):
         # parameters are views of the flat buffers: copy in place so the views stay valid
@@ -340,7 +380,9 @@ class NeRFSystem(nn.Module):
                                perturb=hp["nerf.perturb"] if train else 0, N_importance=hp["nerf.N_importance"],
                                white_back=self.white_back, encode_feat=hp["nerf.feat_dim"] > 0,
                                validation=not train, precision=hp["kernel.precision"], rng=rng,
-                               grad_sink=self._grad_sinks if (train and B == chunk) else None)
+                               grad_sink=self._grad_sinks if (train and B == chunk) else None,
+                               after_fine_bwd=self._reduce_fine_async if (train and B == chunk and self._ddp_active())
+                               else None)
             for k, v in part.items():
                 results[k].append(v)
         results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
@@ -387,8 +429,7 @@ class NeRFSystem(nn.Module):
             # (losses.py:21-64), its backward and psnr (:202-207); autograd continues from the
             # gradients that kernel wrote
             results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng, blend=False)
-            self.group_main.zero_grad()
-            self.group_pose.zero_grad()
+            self._grad_all.zero_()
             if self._tail_ws is None:
                 from .. import _lib as L
                 self._tail_ws = torch.zeros(L.tail_workspace_bytes(), device=rays.device, dtype=torch.uint8)
@@ -411,8 +452,7 @@ class NeRFSystem(nn.Module):
             results = self(rays, batch["feats"], img_idx, sched_mult, rng=rng)
             loss_d = self.loss(results, batch["rgbs"], batch["feats"], depth, sched_mult)
             loss = sum(loss_d.values())
-            self.group_main.zero_grad()
-            self.group_pose.zero_grad()
+            self._grad_all.zero_()
             loss.backward()
             with torch.no_grad():
                 typ = "fine" if self.fine else "coarse"
@@ -420,10 +460,7 @@ class NeRFSystem(nn.Module):
                     psnr_ = -10 * torch.log10(((results[f"s_rgb_{typ}"] - batch["rgbs"]) ** 2).mean())
                 else:
                     psnr_ = torch.zeros(1)
-        if not hp.get("kernel.skip_allreduce", False):      # (bench.py measures the step without it)
-            allreduce_mean_(self.group_main.flat.grad)
-            if hp["pose.optimize"]:
-                allreduce_mean_(self.group_pose.flat.grad)
+        self._reduce_gradients()      # (kernel.skip_allreduce: bench.py measures the step without it)
         live = {"always": True, "never": False, "rgb": sched_mult > 0 or hp["nerf.feat_dim"] <= 0,
                 "cand": sched_mult < 1}
         for opt, sch in zip(self._optimizers, self._schedulers):

@@ -11,7 +11,8 @@ Extra keyword arguments (ours): `precision="bf16"|"fp32"` (default: $UPNERF_PREC
 uniforms the reference would draw for parity tests; `grad_sink=dict(coarse=, fine=,
 coarse_a=, ...)` names fp32 buffers the backward ACCUMULATES parameter / embedding gradients into
 (slices of a flat .grad buffer) instead of returning fresh tensors to autograd;
-`return_depths=dict()` is filled with the sample depths `z_coarse` [R,S] / `z_fine` [R,S+N_importance].
+`after_fine_bwd=callable` is called between the fine and the coarse network's backward (gradient all-reduce
+overlap); `return_depths=dict()` is filled with the sample depths `z_coarse` [R,S] / `z_fine` [R,S+N_importance].
 """
 from __future__ import annotations
 
@@ -178,7 +179,15 @@ class _RenderFn(torch.autograd.Function):
             ga = None if (not wants[which + "_a"] and sink.get(which + "_a") is None) else dest(which + "_a", ea)
             gc = None if (not wants[which + "_c"] and sink.get(which + "_c") is None) else dest(which + "_c", ec)
             io.d_emb_a, io.d_emb_c = L._vp(ga), L._vp(gc)
-        L.render_bwd(a)
+        hook = meta.get("after_fine_bwd")
+        if hook is not None and a.n_importance > 0:
+            # data-parallel training: the fine network's gradients are final after its pass -- the caller's
+            # hook starts their all-reduce, which then runs under the coarse pass
+            L.render_bwd_passes(a, 1)
+            hook()
+            L.render_bwd_passes(a, 2)
+        else:
+            L.render_bwd(a)
         return (None, d_rays, grads.get("coarse"), grads.get("fine"), grads.get("coarse_a"),
                 grads.get("fine_a"), grads.get("coarse_c"), grads.get("fine_c"))
 
@@ -220,7 +229,7 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
                 img_idx=img_idx.contiguous().long(), perturb_rand=as_f32(perturb_rand), u0=as_f32(u0),
                 u1=as_f32(u1), dtype=_dtype_code(kwargs.get("precision") or default_precision()),
                 n_images=0, no_grad=False, grad_sink=kwargs.get("grad_sink"),
-                depths=kwargs.get("return_depths"))
+                depths=kwargs.get("return_depths"), after_fine_bwd=kwargs.get("after_fine_bwd"))
     emb = lambda k: embeddings[k].weight if k in embeddings else None
     ea_c = emb("coarse_a") if coarse.encode_appearance else None
     ec_c = emb("coarse_c") if coarse.encode_candidate else None
