@@ -617,9 +617,11 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
       mbar_init(&bar_pefull[i], 1);
       mbar_init(&bar_peempty[i], 1);
       mbar_init(&bar_tfull[i], 1);
-      mbar_init(&bar_tempty[i], 32);
+      // accumulator drained: my 16 epilogue warps (+ on the leader one relayed arrival for the peer's 16)
+      mbar_init(&bar_tempty[i], 16 + (cta_rank == 0 ? 1 : 0));
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&bar_act[i], 16);
+    // box written: the 8 warps of the owning set (+ on the leader one relayed arrival for the peer's box)
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_act[i], 8 + (cta_rank == 0 ? 1 : 0));
     for (int i = 0; i < 8; ++i) {
       mbar_init(&bar_st[i], 8);
       mbar_init(&bar_stfree[i], kCopyWarps);
@@ -685,19 +687,64 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && cta_rank == 0) {
+    // Warp-uniform loop, one elected lane issues (see the single-tile kernel: a single diverged lane spends
+    // ~200 cycles of address / descriptor arithmetic per MMA, which alone paced this kernel before).
+    if (cta_rank != 0) {
+      // Relay (the peer CTA's otherwise idle MMA warp): the epilogue warps of BOTH CTAs only ever arrive on
+      // barriers of their own CTA -- a cluster-scope release arrive from every epilogue warp (three per warp,
+      // layer and slot) made the epilogue itself ~2x slower.  This warp waits for the peer's local barriers in
+      // the order the leader's issuer consumes them and forwards ONE remote arrival each.
+      const uint32_t act_bar0 = mapa_u32(smem_u32(&bar_act[0]), 0);
+      const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
+      uint32_t act_ph[2] = {0, 0};
+      uint32_t gs = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step) {
+        for (int l = 0; l < kNL; ++l, ++gs) {
+          const LayerDesc& L = args.layer[l];
+          for (int slot = 0; slot < 2; ++slot) {
+            if (gs > 0) {       // (the very first use of an accumulator has no drain to wait for)
+              mbar_wait(&bar_tempty[slot], (gs & 1) ^ 1);
+              if (lane == 0) mbar_arrive_cluster(tempty0 + slot * 8);
+              __syncwarp();
+            }
+            if (L.w_act >= 0) {
+              for (int b = 0; b < 4; ++b) {
+                mbar_wait(&bar_act[slot * 4 + b], act_ph[slot]);
+                if (lane == 0) mbar_arrive_cluster(act_bar0 + (slot * 4 + b) * 8);
+                __syncwarp();
+              }
+              act_ph[slot] ^= 1;
+            }
+          }
+        }
+      }
+    } else {
       const uint32_t idesc = umma_idesc_bf16(2 * kTileM, 256, 0, 0);
       int ws = 0;
       uint32_t wph = 0;
       uint32_t act_ph[2] = {0, 0};
       uint32_t gs = 0;   // layers issued so far per slot (same for both)
       int t = 0;
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) mma_commit_2sm_mc(bar, kMask);
+        __syncwarp();
+      };
       auto next_stage = [&]() {
-        mma_commit_2sm_mc(&bar_wempty[ws], kMask);
+        commit(&bar_wempty[ws]);
         if (++ws == kStages) {
           ws = 0;
           wph ^= 1;
         }
+      };
+      auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t& accum) {
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_bf16_ss_2sm(d, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
+                            umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, (k > 0) ? 1u : accum);
+        }
+        __syncwarp();
+        accum = 1;
       };
       for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
         for (int l = 0; l < kNL; ++l, ++gs) {
@@ -712,16 +759,9 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
               mbar_wait(&bar_pefull[slot], t & 1);
               mbar_wait(&bar_wfull[ws], wph);
               tc_fence_after_sync();
-              const uint32_t a_addr = smem_u32(sPE + slot * kBoxBytes);
-              const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma_bf16_ss_2sm(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                                umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
-                accum = 1;
-              }
+              mma4(d_tmem, smem_u32(sPE + slot * kBoxBytes), smem_u32(sW + ws * kStageBytes), accum);
               next_stage();
-              if (L.pe_last) mma_commit_2sm_mc(&bar_peempty[slot], kMask);
+              if (L.pe_last) commit(&bar_peempty[slot]);
             }
             if (L.w_act >= 0) {
 #pragma unroll 1
@@ -729,19 +769,12 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
                 mbar_wait(&bar_wfull[ws], wph);
                 mbar_wait_cluster(&bar_act[slot * 4 + b], act_ph[slot]);
                 tc_fence_after_sync();
-                const uint32_t a_addr = smem_u32(sAct + slot * kActBytes + b * kBoxBytes);
-                const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  mma_bf16_ss_2sm(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                                  umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, accum);
-                  accum = 1;
-                }
+                mma4(d_tmem, smem_u32(sAct + slot * kActBytes + b * kBoxBytes), smem_u32(sW + ws * kStageBytes), accum);
                 next_stage();
               }
               act_ph[slot] ^= 1;
             }
-            mma_commit_2sm_mc(&bar_tfull[slot], kMask);
+            commit(&bar_tfull[slot]);
           }
         }
       }
@@ -802,8 +835,6 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
     const uint32_t sbias = smem_u32(sBias);
     const uint32_t sheadw = smem_u32(sHeadW);
     const uint32_t swz = row & 7;
-    const uint32_t act_bar0 = mapa_u32(smem_u32(&bar_act[0]), 0);
-    const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
     uint32_t gs = 0;
     uint32_t nst = 0;   // lsu_store == 2: stored layers so far (= releases seen per (slot, box))
     for (int unit = unit0; unit < num_units; unit += unit_step) {
@@ -848,7 +879,7 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
               // my last TMEM read of this layer has landed in registers: the accumulator may be reused
               tc_fence_before_sync();
               __syncwarp();
-              if (lane0) mbar_arrive_cluster(tempty0 + slot * 8);
+              if (lane0) mbar_arrive(&bar_tempty[slot]);
             }
             if (relu) {
 #pragma unroll
@@ -882,7 +913,7 @@ mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_c
               if (feeds) {
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane0) mbar_arrive_cluster(act_bar0 + (slot * 4 + box) * 8);
+                if (lane0) mbar_arrive(&bar_act[slot * 4 + box]);
               }
               if (want_mask)
                 args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;

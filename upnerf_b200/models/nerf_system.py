@@ -225,11 +225,12 @@ class NeRFSystem(nn.Module):
             keys.append(adam_class(f"embedding_{ename}.weight"))
         n_main = sum(p.numel() for p in main)
         n_pose = self.depth_scale.weight.numel() + self.se3_refine.weight.numel()
-        self._grad_all = torch.zeros(n_main + n_pose, device=self._device, dtype=torch.float32)
+        n_pad = (n_main + 63) // 64 * 64          # the pose group starts 256-byte aligned (fused Adam: 16-byte vectors)
+        self._grad_all = torch.zeros(n_pad + n_pose, device=self._device, dtype=torch.float32)
         self.group_main = FlatGroup(main, self._device, keys, grad_storage=self._grad_all[:n_main])
         self.group_pose = FlatGroup([self.depth_scale.weight, self.se3_refine.weight], self._device,
                                     [adam_class("depth_scale.weight"), adam_class("se3_refine.weight")],
-                                    grad_storage=self._grad_all[n_main:])
+                                    grad_storage=self._grad_all[n_pad:])
         self._n_fine = sum(p.numel() for p in self.nerf_fine.parameters()) if self.fine else 0
         self._pending_reduce = None
         # the render backward accumulates straight into these slices of the flat gradient buffer
