@@ -395,6 +395,9 @@ def run_train(args):
 
     # ---- per-kernel-family device time (CUDA events on the launching stream) ------------------
     # (every rank runs these steps: training_step contains the gradient all-reduce, a collective)
+    # (eager launches: the library's per-launch events cannot be recorded inside a replayed graph)
+    graphed = system.hparams["kernel.cuda_graph"]
+    system.hparams["kernel.cuda_graph"] = False
     lib.upnerf_profile_enable(1)
     n_prof = min(K, 5)
     for i in range(n_prof):
@@ -402,6 +405,7 @@ def run_train(args):
     torch.cuda.synchronize()
     prof = collect_profile(lib, L, n_prof)
     lib.upnerf_profile_enable(0)
+    system.hparams["kernel.cuda_graph"] = graphed
 
     # ---- N > 1: the same step without its gradient all-reduce (communication cost, measured) -----
     ms_nocomm = None

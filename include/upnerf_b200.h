@@ -57,6 +57,9 @@ int upnerf_fill_pattern(void* dst, int64_t bytes, uint32_t seed, void* stream);
  * bulk stores in flight per CTA (depth 1 exposes the issue -> shared-memory-read-done latency). */
 int upnerf_tma_store_probe(void* dst, int64_t rows, int64_t ld, int depth /* stores in flight, 1..4 */, void* stream);
 long long upnerf_launch_count(void);
+/* A CUDA graph captured from this library's launches was replayed: credit its `n` kernel nodes to the counter
+ * (the library does not see replays; the host that captured the graph counted the launches under capture). */
+void upnerf_launch_count_add(long long n);
 void upnerf_profile_enable(int on);
 int upnerf_profile_collect(double* ms, long long* launches, double* work, double* bytes, int ncat);
 
@@ -423,6 +426,9 @@ typedef struct upnerf_tail_args {
   float* d_depth_scale;
   void* workspace;
   uint64_t workspace_bytes;
+  const float* sched_mult_dev; /* optional DEVICE scalar: when non-NULL the kernel reads the schedule multiplier from
+                                  it instead of `sched_mult` (CUDA-graph replay: the host rewrites it every step;
+                                  `sched_mult` must still lie in the same phase -- 0, (0,1) or 1 -- as the value) */
 } upnerf_tail_args;
 uint64_t upnerf_tail_workspace_bytes(void);
 int upnerf_tail_loss(const upnerf_tail_args* a, void* stream);
@@ -450,6 +456,9 @@ typedef struct upnerf_adam_args {
   double beta1, beta2, eps;   /* doubles: 1 - beta is rounded to fp32 from the double, as torch does */
   double decay_mul;           /* AdamW (tto, models/nerf_system_optmize.py:61): params *= 1 - lr*weight_decay
                                  before the update, as torch.optim.AdamW does; 0 or 1 = plain Adam */
+  const float* dev_scalars;   /* optional DEVICE array [2*UPNERF_ADAM_MAX_SEGMENTS + 1] = seg_step_size | seg_bc2_sqrt |
+                                 decay_mul: when non-NULL it overrides the three by-value fields, so a captured CUDA
+                                 graph of the step can be replayed with the host rewriting the scalars every step */
 } upnerf_adam_args;
 int upnerf_adam_step(const upnerf_adam_args* a, void* stream);
 

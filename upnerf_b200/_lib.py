@@ -76,6 +76,14 @@ def launch_count() -> int:
     return int(f())
 
 
+def launch_count_add(n: int) -> None:
+    """Credit the kernel nodes of a replayed CUDA graph (captured from this library's launches)."""
+    f = lib().upnerf_launch_count_add
+    f.argtypes = [C.c_longlong]
+    f.restype = None
+    f(int(n))
+
+
 def stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -211,7 +219,7 @@ class TailArgs(C.Structure):
     _fields_ = ([("n_rays", C.c_int64), ("feat_dim", C.c_int), ("has_fine", C.c_int), ("sched_mult", C.c_float),
                  ("depth_mult", C.c_float), ("alpha_reg", C.c_float), ("near_", C.c_float), ("far_", C.c_float)]
                 + [(n, C.c_void_p) for n in _TAIL_IN + _TAIL_OUT]
-                + [("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)])
+                + [("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("sched_mult_dev", C.c_void_p)])
 
 
 TNET_PARAMS = 19
@@ -263,7 +271,8 @@ class AdamArgs(C.Structure):
                 ("n", C.c_int64), ("n_segments", C.c_int),
                 ("seg_end", C.c_int64 * ADAM_MAX_SEGMENTS), ("seg_step_size", C.c_float * ADAM_MAX_SEGMENTS),
                 ("seg_bc2_sqrt", C.c_float * ADAM_MAX_SEGMENTS), ("seg_live", C.c_int * ADAM_MAX_SEGMENTS),
-                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("decay_mul", C.c_double)]
+                ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("decay_mul", C.c_double),
+                ("dev_scalars", C.c_void_p)]
 
 
 def adam_step(a: AdamArgs):

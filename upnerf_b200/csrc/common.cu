@@ -102,6 +102,7 @@ LaunchScope::~LaunchScope() {
 extern "C" {
 
 long long upnerf_launch_count(void) { return upnerf::g_launches; }
+void upnerf_launch_count_add(long long n) { upnerf::g_launches += n; }
 
 void upnerf_profile_enable(int on) {
   upnerf::g_prof.enabled = on != 0;

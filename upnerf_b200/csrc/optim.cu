@@ -42,13 +42,22 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = p - step_size * __fdiv_rn(m, denom);            // param.addcdiv_(exp_avg, denom, -step_size)
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ upnerf_adam_args a, const Betas k) {
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ upnerf_adam_args a, const Betas k0) {
   const int64_t i0 = (blockIdx.x * 256ll + threadIdx.x) * 4;
   if (i0 >= a.n) return;
+  // per-step scalars: by value, or (CUDA-graph replay) from the device array the host rewrites every step
+  const float* ds = a.dev_scalars;
+  Betas k = k0;
+  if (ds) {
+    const float d = __ldg(ds + 2 * UPNERF_ADAM_MAX_SEGMENTS);
+    k.decay = (d == 0.f) ? 1.f : d;
+  }
+  auto step_size = [&](int s) { return ds ? __ldg(ds + s) : a.seg_step_size[s]; };
+  auto bc2_sqrt = [&](int s) { return ds ? __ldg(ds + UPNERF_ADAM_MAX_SEGMENTS + s) : a.seg_bc2_sqrt[s]; };
   const int s0 = find_segment(a, i0);
   if (i0 + 4 <= a.seg_end[s0] && i0 + 4 <= a.n) {
     if (!a.seg_live[s0]) return;
-    const float ss = a.seg_step_size[s0], bc = a.seg_bc2_sqrt[s0];
+    const float ss = step_size(s0), bc = bc2_sqrt(s0);
     float4 p = *reinterpret_cast<float4*>(a.params + i0);
     const float4 g = *reinterpret_cast<const float4*>(a.grads + i0);
     float4 m = *reinterpret_cast<float4*>(a.exp_avg + i0);
@@ -66,7 +75,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ upner
   for (int64_t i = i0; i < i0 + 4 && i < a.n; ++i) {   // a group of four straddling a boundary
     while (a.seg_end[s] <= i) ++s;
     if (!a.seg_live[s]) continue;
-    adam_one(a.params[i], a.grads[i], a.exp_avg[i], a.exp_avg_sq[i], k, a.seg_step_size[s], a.seg_bc2_sqrt[s]);
+    adam_one(a.params[i], a.grads[i], a.exp_avg[i], a.exp_avg_sq[i], k, step_size(s), bc2_sqrt(s));
   }
 }
 

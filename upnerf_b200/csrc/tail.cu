@@ -40,7 +40,7 @@ tail_loss_kernel(const __grid_constant__ upnerf_tail_args a, float* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t R = a.n_rays;
   const int F = a.feat_dim;
-  const float m = a.sched_mult;
+  const float m = a.sched_mult_dev ? __ldg(a.sched_mult_dev) : a.sched_mult;
   const bool lo = m < 1.f, hi = m > 0.f;
   const bool fine = a.has_fine != 0;
   const float invR = 1.f / static_cast<float>(R);

@@ -45,12 +45,15 @@ _TAIL_KEYS = (("s_depth_c", "s_depth_coarse"), ("s_depth_f", "s_depth_fine"), ("
 _NO_GRAD = ("t_weight_c", "t_weight_f")     # detached in the reference (losses.py:28,47)
 
 
-def fused_tail(results, batch, depth_scale, sched_mult, *, depth_mult, alpha_reg, near, far, fine, workspace):
+def fused_tail(results, batch, depth_scale, sched_mult, *, depth_mult, alpha_reg, near, far, fine, workspace,
+               sched_mult_dev=None):
     """One launch for models/nerf_system.py:169-177 + losses.py:21-64 (+ backward) + psnr.
 
     Returns (losses[16] device tensor -- see `upnerf_tail_loss`, roots, grads): `roots[i]` is the
     tensor of `results` whose gradient (for d loss = 1) is `grads[i]`;
     d loss / d depth_scale is accumulated straight into `depth_scale.grad`.
+    `sched_mult_dev` (a CUDA fp32 scalar tensor) makes the kernel read the multiplier from device memory -- a
+    captured step is replayed with a new value each time; `sched_mult` then only selects the phase.
     """
     from . import _lib as L
 
@@ -63,6 +66,11 @@ def fused_tail(results, batch, depth_scale, sched_mult, *, depth_mult, alpha_reg
     a.n_rays, a.feat_dim, a.has_fine = R, batch["feats"].shape[1], int(bool(fine))
     a.sched_mult, a.depth_mult, a.alpha_reg, a.near_, a.far_ = sched_mult, depth_mult, alpha_reg, near, far
     keep = []
+    if sched_mult_dev is not None:
+        if not sched_mult_dev.is_cuda or sched_mult_dev.dtype != torch.float32:
+            raise L.UpnerfError("fused_tail: sched_mult_dev must be a CUDA fp32 tensor")
+        keep.append(sched_mult_dev)
+        a.sched_mult_dev = sched_mult_dev.data_ptr()
 
     def f32(t):
         t = t.detach()

@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 from torch import nn
 
+from .. import _lib as _L
 from ..losses import UPNeRFLoss, fused_tail
 from ..optim import FlatAdam
 from ..utils import ray as ray_utils
@@ -53,6 +54,10 @@ def default_hparams() -> dict:
         # TransientNet on a second CUDA stream beside the render (UPNERF_TNET_SIDE=0 turns it off)
         "kernel.side_stream": os.environ.get("UPNERF_TNET_SIDE", "1") != "0",
         "kernel.fused_tail": True,      # depth correction + loss + its backward + psnr as one launch (CUDA only)
+        # the whole optimisation step as ONE CUDA-graph replay (UPNERF_CUDA_GRAPH=0 turns it off); the first
+        # `kernel.cuda_graph_warmup` steps run eagerly (lazy initialisation must not happen under capture)
+        "kernel.cuda_graph": os.environ.get("UPNERF_CUDA_GRAPH", "1") != "0",
+        "kernel.cuda_graph_warmup": 3,
     }
 
 
@@ -162,6 +167,9 @@ class NeRFSystem(nn.Module):
         self._tail_ws = None
         self._side_stream = None
         self._steps_seen = 0
+        self._graphs = {}               # key -> _StepGraph (captured optimisation steps)
+        self._graph_pool = None
+        self.graph_replays = 0
         if self.hparams["nerf.feat_dim"] <= 0 and self.hparams["nerf.candidate_dim"] > 0:
             raise NotImplementedError(
                 "upnerf_b200: encode_feat=False (nerf.feat_dim <= 0) together with a candidate head -- the "
@@ -344,10 +352,13 @@ class NeRFSystem(nn.Module):
                 keys += [f"l_rgb_{tag}"] + (["l_beta", "l_alpha"] if tag == "f" else [])
         return keys
 
-    def set_progress(self, progress: float):
+    def set_progress(self, progress: float, fill=True):
         # the reference keeps progress in an fp32 Parameter and reads it back with .item()
         # (models/nerf_system.py:180,220-226): the schedule sees the fp32-rounded value
+        # (`fill=False`: the graphed step has already written the device copies)
         self._progress = float(torch.tensor(float(progress), dtype=torch.float32))
+        if not fill:
+            return
         self.nerf_coarse.progress.data.fill_(self._progress)
         if self.fine:
             self.nerf_fine.progress.data.fill_(self._progress)
@@ -403,6 +414,18 @@ class NeRFSystem(nn.Module):
         return results
 
     # ------------------------------------------------------------------ one optimisation step
+    def _check_batch(self, img_idx):
+        """Cheap invariants, checked on the first step and then rarely (one host sync): indices in range
+        (nn.Embedding would raise; the kernels index raw tables) and the flat-buffer aliasing."""
+        if img_idx.numel() and not (0 <= int(img_idx.min()) and int(img_idx.max()) < self.N_images):
+            raise IndexError(f"img_idx out of range [0, {self.N_images})")
+        self.group_main.check()
+        self.group_pose.check()
+
+    def _live_classes(self, sched_mult):
+        return {"always": True, "never": False, "rgb": sched_mult > 0 or self.hparams["nerf.feat_dim"] <= 0,
+                "cand": sched_mult < 1}
+
     def training_step(self, batch, batch_nb=0, rng=None):
         """models/nerf_system.py:150-229."""
         hp = self.hparams
@@ -411,20 +434,49 @@ class NeRFSystem(nn.Module):
             img_idx = img_idx.contiguous().long()       # the kernels read int64 indices
             batch = dict(batch, img_idx=img_idx)
         if self._steps_seen % 256 == 0:
-            # cheap invariants, checked on the first step and then rarely (one host sync): indices in range
-            # (nn.Embedding would raise; the kernels index raw tables) and the flat-buffer aliasing
-            if img_idx.numel() and not (0 <= int(img_idx.min()) and int(img_idx.max()) < self.N_images):
-                raise IndexError(f"img_idx out of range [0, {self.N_images})")
-            self.group_main.check()
-            self.group_pose.check()
+            self._check_batch(img_idx)
         self._steps_seen += 1
+        sched_mult = self.get_schedule_mult(self._progress)
+        if (hp["kernel.cuda_graph"] and hp["kernel.fused_tail"] and rng is None and img_idx.is_cuda
+                and self._steps_seen > hp["kernel.cuda_graph_warmup"] and torch.is_grad_enabled()
+                and (not self._ddp_active() or hp.get("kernel.cuda_graph_ddp", False))):
+            return self._training_step_graphed(batch, sched_mult)
+        loss, loss_d, psnr_ = self._step_body(batch, sched_mult, rng=rng)
+        for opt in self._optimizers:
+            if isinstance(opt, FlatAdam):
+                opt.set_live(self._live_classes(sched_mult))
+            opt.step()
+        return self._finish_step(loss, loss_d, psnr_)
+
+    def _finish_step(self, loss, loss_d, psnr_):
+        """Host bookkeeping of a step: learning-rate schedules, logging, step counters, progress."""
+        hp = self.hparams
+        for opt, sch in zip(self._optimizers, self._schedulers):
+            opt._opt_called = True          # (the graphed step launches the update itself, not through opt.step)
+            sch.step()
+        self.log("train/loss", loss.detach())
+        for k, v in loss_d.items():
+            self.log(f"train/{k}", v.detach())
+        self.log("train/psnr", psnr_)
+        self.global_step += len(self._optimizers)
+        if hp["pose.optimize"]:
+            self.set_progress(self.global_step / (hp["max_steps"] * 2), fill=not self._in_graph_step)
+        return loss
+
+    _in_graph_step = False
+
+    def _step_body(self, batch, sched_mult, rng=None, scal=None):
+        """Pose refinement -> render -> TransientNet -> loss -> backward -> gradient mean: everything of a step
+        that runs on the device before the optimiser update.  `scal` (graph capture): device tensor holding the
+        per-step scalars, [0] = sched_mult."""
+        hp = self.hparams
+        img_idx = batch["img_idx"]
         if hp["pose.optimize"]:
             rays = ray_utils.refine_rays(self.se3_refine.weight, img_idx, batch["c2w"], batch["directions"],
                                          batch["ray_infos"])
         else:
             o, d = ray_utils.get_rays(batch["directions"], batch["c2w"])
             rays = torch.cat([o, d, batch["ray_infos"]], 1)
-        sched_mult = self.get_schedule_mult(self._progress)
         if hp["kernel.fused_tail"] and rays.is_cuda:
             # render + TransientNet, then ONE launch for the depth correction (:169-177), UPNeRFLoss
             # (losses.py:21-64), its backward and psnr (:202-207); autograd continues from the
@@ -437,7 +489,8 @@ class NeRFSystem(nn.Module):
             losses, roots, grads = fused_tail(results, batch, self.depth_scale.weight, sched_mult,
                                               depth_mult=hp["loss.depth_mult"], alpha_reg=hp["loss.alpha_reg"],
                                               near=hp["nerf.near"], far=hp["nerf.far"], fine=self.fine,
-                                              workspace=self._tail_ws)
+                                              workspace=self._tail_ws,
+                                              sched_mult_dev=None if scal is None else scal[0:1])
             torch.autograd.backward(roots, grads)
             from .._lib import TAIL_TERMS
             live = self._live_terms(sched_mult)
@@ -462,19 +515,87 @@ class NeRFSystem(nn.Module):
                 else:
                     psnr_ = torch.zeros(1)
         self._reduce_gradients()      # (kernel.skip_allreduce: bench.py measures the step without it)
-        live = {"always": True, "never": False, "rgb": sched_mult > 0 or hp["nerf.feat_dim"] <= 0,
-                "cand": sched_mult < 1}
-        for opt, sch in zip(self._optimizers, self._schedulers):
-            if isinstance(opt, FlatAdam):
-                opt.set_live(live)
-            opt.step()
-            sch.step()
+        return loss, loss_d, psnr_
 
-        self.log("train/loss", loss.detach())
-        for k, v in loss_d.items():
-            self.log(f"train/{k}", v.detach())
-        self.log("train/psnr", psnr_)
-        self.global_step += len(self._optimizers)
+    # ------------------------------------------------------------------ the step as one CUDA-graph replay
+    # (reference loop models/nerf_system.py:150-229.)  Everything the host decides per step
+    # and that changes continuously -- sched_mult in the loss weights, `progress`, both optimisers' step sizes and
+    # bias corrections -- lives in a small device array the host refreshes with one small copy before each replay
+    # (from pageable memory: staged at call time, so the host may run ahead of the device); everything discrete (schedule phase, the static/candidate split of the fine samples, live parameter
+    # classes, batch shapes) is the key under which a graph is captured.
+    def _graph_key(self, batch, sched_mult):
+        hp = self.hparams
+        phase = 0 if sched_mult == 0 else (2 if sched_mult == 1 else 1)
+        two = self.fine and hp["nerf.candidate_dim"] > 0 and 0 < sched_mult < 1
+        n_static = round(sched_mult * hp["nerf.N_importance"]) if two else 0
+        flags = tuple(tuple(o.live_flags()) for o in self._optimizers if isinstance(o, FlatAdam))
+        shapes = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()) if torch.is_tensor(v))
+        return (phase, n_static, flags, shapes, self._ddp_active(), bool(hp.get("kernel.skip_allreduce", False)))
+
+    def _training_step_graphed(self, batch, sched_mult):
+        hp = self.hparams
+        for opt in self._optimizers:
+            opt.set_live(self._live_classes(sched_mult))
+        key = self._graph_key(batch, sched_mult)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture_step(batch, sched_mult)
+            if len(self._graphs) >= 4:            # keep a few phases' graphs; they share one memory pool
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g
+        # host half of the step: the scalars of THIS step
+        n_sc = FlatAdam.N_SCALARS
+        h = [0.0] * (2 + n_sc * len(self._optimizers))
+        h[0] = sched_mult
+        next_progress = self._progress
         if hp["pose.optimize"]:
-            self.set_progress(self.global_step / (hp["max_steps"] * 2))
-        return loss
+            gs = self.global_step + len(self._optimizers)
+            next_progress = float(torch.tensor(gs / (hp["max_steps"] * 2), dtype=torch.float32))
+        h[1] = next_progress
+        for j, opt in enumerate(self._optimizers):
+            _, vals = opt.advance()
+            h[2 + j * n_sc: 2 + (j + 1) * n_sc] = vals
+        g["scal"].copy_(torch.tensor(h, dtype=torch.float32), non_blocking=True)
+        for k, dst in g["batch"].items():
+            src = batch[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g["graph"].replay()
+        self.graph_replays += 1
+        _L.launch_count_add(g["launches"])
+        out = g["losses"].clone()             # the static output is overwritten by the next replay
+        loss_d = {k: out[i] for k, i in g["loss_idx"].items()}
+        self._in_graph_step = True
+        try:
+            return self._finish_step(out[8], loss_d, out[9])
+        finally:
+            self._in_graph_step = False
+
+    def _capture_step(self, batch, sched_mult):
+        dev = self._device
+        n_sc = FlatAdam.N_SCALARS
+        n_opt = len(self._optimizers)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        static = {k: torch.empty_like(v) for k, v in batch.items() if torch.is_tensor(v)}
+        for k, v in static.items():
+            v.copy_(batch[k])
+        scal = torch.zeros(2 + n_opt * n_sc, device=dev, dtype=torch.float32)
+        flags = [opt.live_flags() for opt in self._optimizers]
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        launches0 = _L.launch_count()
+        with torch.cuda.graph(graph, pool=self._graph_pool):
+            loss, loss_d, psnr_ = self._step_body(static, sched_mult, scal=scal)
+            losses = loss._base if loss._base is not None else loss
+            for j, opt in enumerate(self._optimizers):
+                opt.launch(flags[j], dev_scalars=scal[2 + j * n_sc: 2 + (j + 1) * n_sc])
+            if self.hparams["pose.optimize"]:
+                self.nerf_coarse.progress.data.copy_(scal[1:2].view_as(self.nerf_coarse.progress.data))
+                if self.fine:
+                    self.nerf_fine.progress.data.copy_(scal[1:2].view_as(self.nerf_fine.progress.data))
+        from .._lib import TAIL_TERMS
+        live = self._live_terms(sched_mult)
+        return {"graph": graph, "batch": static, "scal": scal, "losses": losses,
+                "launches": _L.launch_count() - launches0,
+                "loss_idx": {k: i for i, k in enumerate(TAIL_TERMS) if k in live}}

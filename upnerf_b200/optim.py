@@ -47,33 +47,69 @@ class FlatAdam(torch.optim.Optimizer):
             if k in self.live:
                 self.live[k] = bool(v)
 
-    @torch.no_grad()
-    def step(self, closure=None):
+    N_SCALARS = 2 * L.ADAM_MAX_SEGMENTS + 1      # seg_step_size | seg_bc2_sqrt | decay_mul
+
+    def advance(self):
+        """Host half of one step: bump the step counter of every live class and return the per-segment
+        scalars of THIS step as (live flags, [N_SCALARS] floats: step_size | bc2_sqrt | decay_mul)."""
         group = self.param_groups[0]
-        flat = group["params"][0]
-        if flat.grad is None:
-            return None
-        st = self.state[flat]
         b1, b2 = group["betas"]
         lr = float(group["lr"])
         for k, alive in self.live.items():
             if alive:
                 self.class_steps[k] += 1
+        M = L.ADAM_MAX_SEGMENTS
+        vals = [0.0] * self.N_SCALARS
+        flags = []
+        for i, (_, key) in enumerate(self.segments):
+            alive = self.live[key] and self.class_steps[key] > 0
+            flags.append(int(alive))
+            if alive:
+                t = self.class_steps[key]
+                vals[i] = lr / (1.0 - b1 ** t)
+                vals[M + i] = math.sqrt(1.0 - b2 ** t)
+        vals[2 * M] = 1.0 - lr * float(group.get("weight_decay", 0.0))
+        return flags, vals
+
+    def launch(self, flags, vals=None, dev_scalars=None):
+        """Device half: one `upnerf_adam_step`.  The scalars go by value (`vals`) or -- inside a captured
+        CUDA graph -- are read from `dev_scalars` ([N_SCALARS] fp32 on the device, rewritten before every replay)."""
+        group = self.param_groups[0]
+        flat = group["params"][0]
+        st = self.state[flat]
+        b1, b2 = group["betas"]
+        M = L.ADAM_MAX_SEGMENTS
         a = L.AdamArgs()
         a.params, a.grads = flat.data_ptr(), flat.grad.data_ptr()
         a.exp_avg, a.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
         a.n, a.n_segments = flat.numel(), len(self.segments)
-        for i, (end, key) in enumerate(self.segments):
+        for i, (end, _) in enumerate(self.segments):
             a.seg_end[i] = end
-            alive = self.live[key] and self.class_steps[key] > 0
-            a.seg_live[i] = int(alive)
-            if alive:
-                t = self.class_steps[key]
-                a.seg_step_size[i] = lr / (1.0 - b1 ** t)
-                a.seg_bc2_sqrt[i] = math.sqrt(1.0 - b2 ** t)
+            a.seg_live[i] = flags[i]
+            if vals is not None:
+                a.seg_step_size[i] = vals[i]
+                a.seg_bc2_sqrt[i] = vals[M + i]
         a.beta1, a.beta2, a.eps = float(b1), float(b2), float(group["eps"])
-        a.decay_mul = 1.0 - lr * float(group.get("weight_decay", 0.0))
+        if vals is not None:
+            a.decay_mul = vals[2 * M]
+        if dev_scalars is not None:
+            if (not dev_scalars.is_cuda or dev_scalars.dtype != torch.float32 or not dev_scalars.is_contiguous()
+                    or dev_scalars.numel() < self.N_SCALARS):
+                raise L.UpnerfError("FlatAdam.launch: dev_scalars must be a contiguous CUDA fp32 tensor of N_SCALARS")
+            a.dev_scalars = dev_scalars.data_ptr()
         L.adam_step(a)
+
+    def live_flags(self):
+        """Per-segment liveness as the NEXT `advance()` will see it (the part of a step a captured graph bakes in)."""
+        return [int(self.live[key] and self.class_steps[key] + int(self.live[key]) > 0) for _, key in self.segments]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        flat = self.param_groups[0]["params"][0]
+        if flat.grad is None:
+            return None
+        flags, vals = self.advance()
+        self.launch(flags, vals=vals)
         return None
 
     def state_dict(self):
