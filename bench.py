@@ -42,7 +42,7 @@ PROGRESS = 0.30                  # phase 1 (sched_mult = 0.5): the superset of w
 MACS = {0: 755_584, 1: 814_720, 2: 714_240}     # per-sample MACs of the reference MLP
 FLOP_PER_RAY = (S_C + S_C + N_IMP) * MACS[1] * 2 * 3
 CATS = ["gemm_tc", "wgrad_tc", "gemm_simt", "composite", "posenc", "sampling", "pose_rays", "heads", "pack",
-        "trunk_fwd", "trunk_bwd", "wgrad_reduce", "tnet"]
+        "trunk_fwd", "trunk_bwd", "wgrad_reduce", "tnet", "gemm_tf32"]
 TRAIN_METRIC = "train rays/s (fwd+bwd, 64+64 samp/ray)"
 RENDER_METRIC = "inference render rays/s (1920x1080, 64+64 samp/ray, no grad)"
 RENDER_W, RENDER_H, RENDER_CHUNK = 1920, 1080, 4096     # BASELINE config 5; val.chunk_size of configs/default.yaml
@@ -435,7 +435,7 @@ def run_train(args):
     # so HBM bandwidth bounds it.  (Its split-partial reduction is a separate kernel and family.)  The
     # tensor-pipe view of the fused MLP kernels and of all tcgen05 kernels together follows as extra objects.
     roofline = hbm_view("wgrad_tc", "wgrad_tc_kernel")
-    all_tc = ["gemm_tc", "wgrad_tc", "trunk_fwd", "trunk_bwd", "tnet"]
+    all_tc = ["gemm_tc", "wgrad_tc", "trunk_fwd", "trunk_bwd", "tnet", "gemm_tf32"]
     roofline_mlp = {
         "fused_trunk": tensor_view(["trunk_fwd", "trunk_bwd"], "mlp_trunk_fwd_kernel + mlp_trunk_bwd_kernel"),
         "fused_trunk_fwd": tensor_view(["trunk_fwd"], "mlp_trunk_fwd_kernel"),

@@ -189,6 +189,16 @@ int upnerf_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, in
                     int64_t K, const upnerf_epilogue* ep, int accumulate, int split_k,
                     void* stream);
 
+/* The same product on tcgen05 with tf32 operands (fp32 in memory, rounded to nearest tf32 -- 10-bit mantissa -- when
+ * a tile is staged; fp32 accumulate, fp32 out): the production (bf16-mode) path of the small per-ray and
+ * parameter-space products -- per-ray head biases (models/nerf.py:97-113 on the embeddings of
+ * models/rendering.py:255-258), the feature projections after compositing (models/nerf.py:53,76) and their
+ * gradients.  Same strides / split_k / accumulate semantics as upnerf_gemm_f32; the epilogue supports bias and the
+ * rank-1 term only (anything else returns UPNERF_ERR_BAD_CONFIG). */
+int upnerf_gemm_tf32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
+                     int64_t scm, int64_t scn, int64_t M, int64_t N, int64_t K, const upnerf_epilogue* ep,
+                     int accumulate, int split_k, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (a) Pose refinement + ray casting.
  * Replaces, per ray: se3_refine(img_idx) -> Lie.se3_to_SE3 (utils/camera.py:87-98),

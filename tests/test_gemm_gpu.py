@@ -284,3 +284,82 @@ def test_mlp_trunk_bwd_fused(cuda_dev, M):
         assert err <= 0.02 * max(y.abs().max().item(), 1.0), (j, err)
         assert ((got != 0) <= (outs[7 - j].float() > 0)).all(), j      # the mask is exact
         cur = got                                        # chain on the kernel's own bf16 output
+
+
+def _tf32_round(x):
+    """Round-to-nearest (ties away) to tf32's 10-bit mantissa, as cvt.rna.tf32.f32 does."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("case", ["nt", "nn", "tn_split", "tn_big", "vec_m1", "outer_k1", "n16", "col_major_out"])
+def test_gemm_tf32_strided(cuda_dev, case):
+    """upnerf_gemm_tf32 (tcgen05 kind::tf32, thread-staged operands of any stride) against an fp64 product of the
+    tf32-rounded operands (tight) and of the raw operands (tf32 resolution) -- the shapes and stride patterns of
+    the per-ray / parameter-space products in render.cu."""
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(21)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(cuda_dev)
+    split, acc, ep, sc = 1, False, None, None
+    if case == "nt":            # per-ray bias: C[R,128] = P[R,75] W[128, cols]^T + b   (W a column slice: ld > K)
+        M, N, K = 4096 + 37, 128, 75
+        A = rnd(M, K); Wfull = rnd(N, 459); B = Wfull[:, 384:]
+        sa, sb = (K, 1), (459, 1); ref_ops = (A, B.t())
+        bias = rnd(N); ep = L.make_epilogue(bias=bias)
+    elif case == "nn":          # data gradient: gHFr[R,256] = gf[R,384] Wsf[384,256]
+        M, N, K = 1000, 256, 384
+        A = rnd(M, K); B = rnd(K, N)
+        sa, sb = (K, 1), (1, N); ref_ops = (A, B)
+    elif case == "tn_split":    # weight gradient over rays with atomics: dW[384,256] += gf[R,384]^T HFr[R,256]
+        M, N, K = 384, 256, 4096
+        A = rnd(K, M); B = rnd(K, N)
+        sa, sb = (1, M), (1, N); ref_ops = (A.t(), B); split = 32
+    elif case == "tn_big":      # odd sizes, K not a multiple of the split or of 32
+        M, N, K = 130, 77, 1001
+        A = rnd(K, M); B = rnd(K, N)
+        sa, sb = (1, M), (1, N); ref_ops = (A.t(), B); split = 7
+    elif case == "vec_m1":      # bq_const[128] = b_sf[384] W[128,384]^T + b   (M = 1, broadcast row stride)
+        M, N, K = 1, 128, 384
+        A = rnd(1, K); B = rnd(N, K)
+        sa, sb = (0, 1), (K, 1); ref_ops = (A, B.t())
+        bias = rnd(N); ep = L.make_epilogue(bias=bias); acc = True
+    elif case == "outer_k1":    # rank-1 update, K = 1, accumulate
+        M, N, K = 128, 384, 1
+        A = rnd(M, 1); B = rnd(N, 1)
+        sa, sb = (1, 0), (1, 0); ref_ops = (A, B.t()); acc = True
+    elif case == "n16":         # dCrows[R,16] = dBc[R,128] W[128, 256:272]  (narrow output, strided B)
+        M, N, K = 4096, 16, 128
+        A = rnd(M, K); Wfull = rnd(K, 272); B = Wfull[:, 256:]
+        sa, sb = (K, 1), (1, 272); ref_ops = (A, B)
+    else:                       # transposed (column-major) output + rank-1 term
+        M, N, K = 200, 300, 64
+        A = rnd(M, K); B = rnd(N, K)
+        sa, sb = (K, 1), (K, 1); ref_ops = (A, B.t())
+        r1r, r1c = rnd(M), rnd(N); ep = L.make_epilogue(rank1_row=r1r, rank1_col=r1c)
+        sc = (1, M)
+    init = rnd(N, M).t() if sc else rnd(M, N)
+    Cout = init.clone() if (acc or split > 1) else torch.full_like(init, 7.0)
+    if sc is None:
+        sc = (N, 1)
+    else:
+        Cout = Cout.t().contiguous().t()          # [M,N] view of a column-major buffer
+        init = Cout.clone()
+    L.gemm_tf32(A, sa, B, sb, Cout, sc, M, N, K, ep=ep, accumulate=acc, split_k=split)
+    torch.cuda.synchronize()
+    extra = torch.zeros(M, N, device=cuda_dev, dtype=torch.float64)
+    if case in ("nt", "vec_m1"):
+        extra = extra + bias.double()
+    if case == "col_major_out":
+        extra = extra + r1r.double()[:, None] * r1c.double()[None, :]
+    if acc or split > 1:
+        extra = extra + init.double()
+    a64, b64 = ref_ops[0].double(), ref_ops[1].double()
+    ref_exact = a64 @ b64 + extra
+    ref_tf32 = _tf32_round(ref_ops[0].contiguous()).double() @ _tf32_round(ref_ops[1].contiguous()).double() + extra
+    scale = float((a64.abs() @ b64.abs()).max()) + 1.0
+    err_t = float((Cout.double() - ref_tf32).abs().max()) / scale
+    err_e = float((Cout.double() - ref_exact).abs().max()) / scale
+    print(f"{case}: vs tf32-rounded operands {err_t:.2e}, vs exact {err_e:.2e}")
+    assert err_t <= 2e-6, err_t          # fp32 accumulation of exact tf32 products
+    assert err_e <= 1e-3, err_e          # tf32 operand resolution (2^-11 per operand)

@@ -28,6 +28,23 @@ def main():
         if a.startswith("M="):
             M = int(a[2:])
     only_trunk = "trunk" in sys.argv[1:]
+    if "tf32" in sys.argv[1:]:      # the small per-ray / parameter-space products (render.cu), one launch each
+        R = 4096
+        for name, (Mm, Nn, Kk), sa, sb, split, acc in [
+                ("feat = HFr Wsf^T", (R, 384, 256), (256, 1), (256, 1), 1, False),
+                ("gHFr = gf Wsf", (R, 256, 384), (384, 1), (1, 256), 1, False),
+                ("dWsf += gf^T HFr", (384, 256, R), (1, 384), (1, 256), 32, False),
+                ("Bq = P W^T", (R, 128, 75), (75, 1), (459, 1), 1, False),
+                ("Wq32 = Wr0 Wsf", (128, 256, 384), (459, 1), (1, 256), 1, False),
+                ("gWr0 += dWq Wsf^T", (128, 384, 256), (256, 1), (256, 1), 8, True)]:
+            A = torch.randn(max(Mm, Kk) * 512, device=dev)
+            B = torch.randn(max(Nn, Kk) * 512, device=dev)
+            Cc = torch.zeros(Mm, Nn, device=dev)
+            for impl, fn in (("tf32", L.gemm_tf32), ("simt", L.gemm_f32)):
+                ms = timeit(lambda: fn(A, sa, B, sb, Cc, (Nn, 1), Mm, Nn, Kk, accumulate=acc, split_k=split), iters=50)
+                print(f"{impl} {name:22s} M={Mm} N={Nn} K={Kk} split={split}: {ms * 1e3:7.1f} us  "
+                      f"{2.0 * Mm * Nn * Kk / ms / 1e9:6.2f} TFLOP/s")
+        return
     for (N, K, aux) in [] if only_trunk else [(256, 256, 0), (256, 256, 2), (256, 64, 0), (256, 320, 0), (128, 256, 0), (64, 256, 0)]:
         A = torch.randn(M, K, device=dev).bfloat16()
         B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()

@@ -172,6 +172,15 @@ def gemm_f32(A, sa, B, sb, C_out, sc, M, N, K, ep: Epilogue | None = None, accum
     check(st, "upnerf_gemm_f32")
 
 
+def gemm_tf32(A, sa, B, sb, C_out, sc, M, N, K, ep: Epilogue | None = None, accumulate=False, split_k=1):
+    """The same strided product on tcgen05 with tf32 operands (see upnerf_gemm_tf32)."""
+    st = lib().upnerf_gemm_tf32(ptr(A), _i64(sa[0]), _i64(sa[1]), ptr(B), _i64(sb[0]), _i64(sb[1]),
+                                ptr(C_out), _i64(sc[0]), _i64(sc[1]), _i64(M), _i64(N), _i64(K),
+                                C.byref(ep) if ep is not None else None, C.c_int(int(accumulate)),
+                                C.c_int(split_k), stream_ptr())
+    check(st, "upnerf_gemm_tf32")
+
+
 # ---------------------------------------------------------------------------------------
 # Structs of the render-level ABI (mirror include/upnerf_b200.h field for field)
 # ---------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ int sm_count();
 // the launching stream so that bench.py can attribute device time to kernel families.
 enum LaunchCat {
   kCatGemmTc = 0, kCatWgradTc, kCatGemmSimt, kCatComposite, kCatPosenc, kCatSampling,
-  kCatPoseRays, kCatHeads, kCatPack, kCatTrunkFwd, kCatTrunkBwd, kCatWgradReduce, kCatTnet, kNumCats
+  kCatPoseRays, kCatHeads, kCatPack, kCatTrunkFwd, kCatTrunkBwd, kCatWgradReduce, kCatTnet, kCatGemmTf32, kNumCats
 };
 struct LaunchScope {
   int slot;

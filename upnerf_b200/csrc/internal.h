@@ -39,11 +39,26 @@ struct WgradReduceList {
   WgradReduceSlot s[kMaxWgradSlots];
   int n;
 };
+// One weight gradient dW[n, map(k)] += dY^T X, db += colsum(dY) as the launcher takes it.
+struct WgradProblem {
+  const void *dY, *X;
+  int64_t lddy, ldx;
+  float *dW, *dW_hi, *db;
+  int64_t lddw, lddw_hi;
+  int64_t M;
+  int N, K, n_seg;
+  int seg_src[4], seg_len[4], seg_dst[4];
+};
 struct WgradBatch {
   WgradReduceList list;
   float* pool;
   uint64_t pool_floats, used;
   int blocks;
+  // defer != 0: wgrad_launch() only queues the problem; wgrad_reduce() (or a full queue) launches all queued
+  // problems as ONE grouped kernel whose grid is shared out in proportion to the bytes each one streams
+  int defer;
+  int n_pending;
+  WgradProblem pending[kMaxWgradSlots];
 };
 // Upper bound of the pool one network pass of the D=8, W=256 architecture needs (floats).
 uint64_t wgrad_pool_floats();
@@ -51,6 +66,7 @@ int wgrad_launch(const void* dY, int64_t lddy, const void* X, int64_t ldx, float
                  float* dW_hi, int64_t lddw_hi, float* db, int64_t M, int N, int K, int n_seg,
                  const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
                  WgradBatch* batch, void* stream);
+int wgrad_flush(WgradBatch* batch, cudaStream_t st);
 int wgrad_reduce(WgradBatch* batch, cudaStream_t st);
 int gather_rows(const float* table, const int64_t* idx, int64_t R, int dim, float* out, int64_t ld_out,
                 cudaStream_t st);

@@ -396,6 +396,13 @@ int wgrad(const Ctx& c, const void* dY, int64_t lddy, const void* X, int64_t ldx
 int mm(const Ctx& c, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
        float* C, int64_t scm, int64_t scn, int64_t M, int64_t N, int64_t K, const upnerf_epilogue* ep,
        int accumulate, int split_k = 1) {
+  // production mode: tensor cores with tf32 operands; validation mode: fp32 FMA
+  if (c.dtype == UPNERF_BF16) {
+    // an accumulating product without an epilogue may as well be split over K (atomics into the existing
+    // values): the parameter-space chain rules have 1..3 output tiles and would otherwise run 8 K-chunks in a row
+    if (accumulate && !ep && split_k == 1 && K > 32) split_k = static_cast<int>(K / 32 < 8 ? K / 32 : 8);
+    return upnerf_gemm_tf32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
+  }
   return upnerf_gemm_f32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
 }
 // out[n] += sum_m s[m] X[m,n] for fp32 X of any width (falls back to the GEMM for odd widths)
@@ -873,6 +880,9 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // 8. every tcgen05 weight gradient of this pass has parked its split partials: one reduction
   //    launch sums them (fixed order) into the parameter gradients
+  //    (the grouped weight-gradient launch does not depend on the side stream's leaves: it goes first, so they
+  //    keep running beside it; the reduction writes parameter gradients and waits for them)
+  if (c.wb) UPNERF_TRY(wgrad_flush(c.wb, c.st));
   UPNERF_TRY(join_side(c));
   if (c.wb) UPNERF_TRY(wgrad_reduce(c.wb, c.st));
 
@@ -973,6 +983,7 @@ int upnerf_render_bwd_passes(const upnerf_render_args* a, int passes, void* stre
   memset(&wb, 0, sizeof(wb));
   wb.pool = pl.scratch.wg_pool;
   wb.pool_floats = pl.scratch.wg_pool_floats;
+  wb.defer = 1;   // all weight gradients of a pass go out as ONE grouped launch in front of the split reduction
   const Ctx c = make_ctx(a->dtype, pl.es, as_stream(stream), wb.pool ? &wb : nullptr);
   const Phase ph = make_phase(a->cfg, a->sched_mult);
   // A pass none of whose outputs received a gradient contributes exact zeros everywhere (the fine

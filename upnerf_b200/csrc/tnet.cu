@@ -389,6 +389,7 @@ int upnerf_tnet_bwd(const upnerf_tnet_args* a, void* stream) {
   memset(&wb, 0, sizeof(wb));
   wb.pool = p.pool;
   wb.pool_floats = p.pool_floats;
+  wb.defer = 1;   // one grouped launch for all of them
   auto wg = [&](const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, float* db, int N,
                 int K, int dst0) -> int {
     const int src = 0, len = K, dst = dst0;

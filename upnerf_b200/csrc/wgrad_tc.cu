@@ -63,14 +63,32 @@ struct WgradArgs {
   int N;
   int K;
   int splits;
+  int chunks;              // N / 128
   int64_t rows_per_split;  // multiple of kBS
   int n_seg;
   int seg_src[kMaxSeg], seg_len[kMaxSeg], seg_dst[kMaxSeg];
 };
 
+// A launch covers a GROUP of independent weight gradients (all layers of one network pass): the linear block
+// index selects (problem, 128-row chunk, split).  Every problem gets a share of the grid proportional to the
+// bytes it streams, so the whole group is ONE wave of ~sm_count CTAs that finish together -- one ramp-up, one
+// tail and ~8 split partials per layer instead of one launch, one tail and ~74 partials per layer.
+struct WgradGroupParams {
+  CUtensorMap tmY[kMaxWgradSlots];
+  CUtensorMap tmX[kMaxWgradSlots];
+  WgradArgs p[kMaxWgradSlots];
+  int block_begin[kMaxWgradSlots + 1];
+  int n;
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
-                const __grid_constant__ WgradArgs args) {
+wgrad_tc_kernel(const __grid_constant__ WgradGroupParams grp) {
+  int pi = 0;
+  while (pi + 1 < grp.n && static_cast<int>(blockIdx.x) >= grp.block_begin[pi + 1]) ++pi;
+  const WgradArgs& args = grp.p[pi];
+  const CUtensorMap* const tmY = &grp.tmY[pi];
+  const CUtensorMap* const tmX = &grp.tmX[pi];
+  const int local = static_cast<int>(blockIdx.x) - grp.block_begin[pi];
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -85,8 +103,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x;  // which 128 output rows
-  const int split = blockIdx.y;
+  const int chunk = local % args.chunks;  // which 128 output rows
+  const int split = local / args.chunks;
   const int K = args.K;
   const int bboxes = K / 64;
 
@@ -96,8 +114,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   const int nsteps = row_end > row_begin ? static_cast<int>((row_end - row_begin + kBS - 1) / kBS) : 0;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmY);
-    prefetch_tmap(&tmX);
+    prefetch_tmap(tmY);
+    prefetch_tmap(tmX);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
@@ -138,9 +156,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           mbar_arrive_expect_tx(&bar_full[stage], tx);
           uint8_t* base = sStage + stage * kStageBytes;
           for (int j = 0; j < kABoxes; ++j)
-            tma_load_2d(base + j * kBoxBytes, &tmY, &bar_full[stage], chunk * 128 + j * 64, r0);
+            tma_load_2d(base + j * kBoxBytes, tmY, &bar_full[stage], chunk * 128 + j * 64, r0);
           for (int j = 0; j < bboxes; ++j)
-            tma_load_2d(base + (kABoxes + j) * kBoxBytes, &tmX, &bar_full[stage], j * 64, r0);
+            tma_load_2d(base + (kABoxes + j) * kBoxBytes, tmX, &bar_full[stage], j * 64, r0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -195,7 +213,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         // thread = output row: lanes hold consecutive rows, so column-major partials are
         // written as full 128-byte lines straight from the TMEM registers
         float* dst = args.partial +
-                     (static_cast<int64_t>(split) * gridDim.x + chunk) * (K + 1) * 128 + quad * 32 + lane;
+                     (static_cast<int64_t>(split) * args.chunks + chunk) * (K + 1) * 128 + quad * 32 + lane;
         for (int g = 0; g < K / 32; ++g) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + g * 32, v);
@@ -245,7 +263,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   } else if (args.partial && warp >= 2) {
     // a split without rows still owns a slot of the partial buffer
     float* dst = args.partial +
-                 (static_cast<int64_t>(split) * gridDim.x + chunk) * (K + 1) * 128 + (threadIdx.x - 64);
+                 (static_cast<int64_t>(split) * args.chunks + chunk) * (K + 1) * 128 + (threadIdx.x - 64);
     for (int c = 0; c <= K; ++c) dst[c * 128] = 0.f;
   }
 
@@ -313,76 +331,154 @@ extern "C" int upnerf_wgrad2_bf16(const void* dY, int64_t lddy, const void* X, i
   return upnerf::wgrad_launch(dY, lddy, X, ldx, dW_lo, lddw_lo, dW_hi, lddw_hi, nullptr, M, 256, K, n_seg,
                               seg_src_host, seg_len_host, seg_dst_host, nullptr, stream);
 }
+namespace upnerf {
+namespace {
+
+int fill_args(WgradArgs* args, const WgradProblem& q) {
+  UPNERF_REQUIRE(q.M > 0, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: M=%lld", (long long)q.M);
+  UPNERF_REQUIRE(q.N >= 128 && q.N <= 256 && q.N % 128 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "wgrad_bf16: N=%d must be 128 or 256", q.N);
+  UPNERF_REQUIRE(q.K >= 64 && q.K <= kMaxK && q.K % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "wgrad_bf16: K=%d must be a multiple of 64 in [64,320]", q.K);
+  UPNERF_REQUIRE(q.n_seg >= 1 && q.n_seg <= kMaxSeg, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: n_seg=%d", q.n_seg);
+  memset(args, 0, sizeof(*args));
+  args->dW = q.dW;
+  args->lddw = q.lddw;
+  args->dW_hi = q.dW_hi;
+  args->lddw_hi = q.lddw_hi;
+  args->db = q.db;
+  args->M = q.M;
+  args->N = q.N;
+  args->K = q.K;
+  args->chunks = q.N / 128;
+  args->n_seg = q.n_seg;
+  for (int i = 0; i < q.n_seg; ++i) {
+    args->seg_src[i] = q.seg_src[i];
+    args->seg_len[i] = q.seg_len[i];
+    args->seg_dst[i] = q.seg_dst[i];
+    UPNERF_REQUIRE(q.seg_src[i] >= 0 && q.seg_src[i] + q.seg_len[i] <= q.K, UPNERF_ERR_BAD_SHAPE,
+                   "wgrad_bf16: segment %d out of range", i);
+  }
+  return UPNERF_OK;
+}
+
+// One launch for a group of problems.  `batch` (optional) supplies the pool of split partials and collects the
+// reduce slots; without it every CTA adds its tile to dW with atomics.
+int launch_group(const WgradProblem* probs, int n, WgradBatch* batch, cudaStream_t st) {
+  UPNERF_REQUIRE(n >= 1 && n <= kMaxWgradSlots, UPNERF_ERR_BAD_SHAPE, "wgrad group of %d problems", n);
+  static WgradGroupParams* g = nullptr;     // ~6.5 KB of kernel parameters, built in place
+  if (!g) g = static_cast<WgradGroupParams*>(malloc(sizeof(WgradGroupParams)));
+  UPNERF_REQUIRE(g, UPNERF_ERR_WORKSPACE, "wgrad: out of host memory");
+  memset(g, 0, sizeof(*g));
+  g->n = n;
+  // a CTA of problem p streams (128 + K) columns of bf16 per sample row: split the grid in proportion
+  double cost[kMaxWgradSlots], total = 0.0;
+  int64_t steps[kMaxWgradSlots];
+  int splits[kMaxWgradSlots];
+  for (int i = 0; i < n; ++i) {
+    UPNERF_TRY(fill_args(&g->p[i], probs[i]));
+    steps[i] = ceil_div64(probs[i].M, kBS);
+    cost[i] = static_cast<double>(g->p[i].chunks) * (128 + probs[i].K) * static_cast<double>(steps[i]);
+    total += cost[i];
+  }
+  const int T = sm_count();
+  int used = 0;
+  for (int i = 0; i < n; ++i) {
+    int64_t sp = static_cast<int64_t>(T * cost[i] / total / g->p[i].chunks);
+    if (sp > steps[i]) sp = steps[i];
+    if (sp < 1) sp = 1;
+    splits[i] = static_cast<int>(sp);
+    used += splits[i] * g->p[i].chunks;
+  }
+  for (;;) {       // hand the CTAs left over by the rounding to the problems with the longest per-CTA stream
+    int best = -1;
+    double load = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if (splits[i] >= steps[i] || used + g->p[i].chunks > T) continue;
+      const double l = cost[i] / (static_cast<double>(g->p[i].chunks) * splits[i]);
+      if (l > load) { load = l; best = i; }
+    }
+    if (best < 0) break;
+    ++splits[best];
+    used += g->p[best].chunks;
+  }
+  double flop = 0.0, bytes = 0.0;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    WgradArgs& a = g->p[i];
+    const WgradProblem& q = probs[i];
+    a.splits = splits[i];
+    a.rows_per_split = ceil_div64(steps[i], splits[i]) * kBS;
+    g->block_begin[i] = blocks;
+    blocks += splits[i] * a.chunks;
+    if (batch && batch->pool && batch->list.n < kMaxWgradSlots) {
+      const uint64_t need = static_cast<uint64_t>(splits[i]) * a.chunks * (q.K + 1) * 128;
+      if (batch->used + need <= batch->pool_floats) {
+        a.partial = batch->pool + batch->used;
+        batch->used += need;
+        WgradReduceSlot& sl = batch->list.s[batch->list.n++];
+        memset(&sl, 0, sizeof(sl));
+        sl.partial = a.partial;
+        sl.dW = q.dW; sl.lddw = q.lddw; sl.dW_hi = q.dW_hi; sl.lddw_hi = q.lddw_hi; sl.db = q.db;
+        sl.splits = splits[i]; sl.chunks = a.chunks; sl.K = q.K; sl.n_seg = q.n_seg;
+        for (int j = 0; j < q.n_seg; ++j) {
+          sl.seg_src[j] = q.seg_src[j]; sl.seg_len[j] = q.seg_len[j]; sl.seg_dst[j] = q.seg_dst[j];
+        }
+        sl.block_begin = batch->blocks;
+        batch->blocks += a.chunks * (q.K + 1);
+      }
+    }
+    UPNERF_TRY(make_tmap_bf16_2d(&g->tmY[i], q.dY, q.M, q.N, q.lddy, kBS, 64));
+    UPNERF_TRY(make_tmap_bf16_2d(&g->tmX[i], q.X, q.M, q.K, q.ldx, kBS, 64));
+    flop += 2.0 * q.M * q.N * q.K;
+    bytes += 2.0 * q.M * (q.N + q.K) + 4.0 * q.N * q.K;
+  }
+  g->block_begin[n] = blocks;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  LaunchScope scope(kCatWgradTc, st, flop, bytes);
+  wgrad_tc_kernel<<<blocks, kThreads, kSmemBytes, st>>>(*g);
+  UPNERF_CHECK_LAUNCH("wgrad_tc_kernel");
+  return UPNERF_OK;
+}
+
+}  // namespace
+}  // namespace upnerf
+
 int upnerf::wgrad_launch(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
                          float* dW_hi, int64_t lddw_hi, float* db, int64_t M, int N, int K, int n_seg,
                          const int* seg_src_host, const int* seg_len_host, const int* seg_dst_host,
                          WgradBatch* batch, void* stream) {
   using namespace upnerf;
-  UPNERF_REQUIRE(M > 0, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: M=%lld", (long long)M);
-  UPNERF_REQUIRE(N >= 128 && N <= 256 && N % 128 == 0, UPNERF_ERR_BAD_SHAPE,
-                 "wgrad_bf16: N=%d must be 128 or 256", N);
-  UPNERF_REQUIRE(K >= 64 && K <= kMaxK && K % 64 == 0, UPNERF_ERR_BAD_SHAPE,
-                 "wgrad_bf16: K=%d must be a multiple of 64 in [64,320]", K);
-  UPNERF_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: n_seg=%d",
-                 n_seg);
-  WgradArgs args;
-  memset(&args, 0, sizeof(args));
-  args.dW = dW;
-  args.lddw = lddw;
-  args.dW_hi = dW_hi;
-  args.lddw_hi = lddw_hi;
-  args.db = db;
-  args.M = M;
-  args.N = N;
-  args.K = K;
-  args.n_seg = n_seg;
+  UPNERF_REQUIRE(n_seg >= 1 && n_seg <= kMaxSeg, UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: n_seg=%d", n_seg);
+  WgradProblem q;
+  memset(&q, 0, sizeof(q));
+  q.dY = dY; q.lddy = lddy; q.X = X; q.ldx = ldx;
+  q.dW = dW; q.lddw = lddw; q.dW_hi = dW_hi; q.lddw_hi = lddw_hi; q.db = db;
+  q.M = M; q.N = N; q.K = K; q.n_seg = n_seg;
   for (int i = 0; i < n_seg; ++i) {
-    args.seg_src[i] = seg_src_host[i];
-    args.seg_len[i] = seg_len_host[i];
-    args.seg_dst[i] = seg_dst_host[i];
-    UPNERF_REQUIRE(seg_src_host[i] >= 0 && seg_src_host[i] + seg_len_host[i] <= K,
-                   UPNERF_ERR_BAD_SHAPE, "wgrad_bf16: segment %d out of range", i);
+    q.seg_src[i] = seg_src_host[i]; q.seg_len[i] = seg_len_host[i]; q.seg_dst[i] = seg_dst_host[i];
   }
-  const int chunks = N / 128;
-  int splits = sm_count() / chunks;
-  const int64_t steps = ceil_div64(M, kBS);
-  if (splits > steps) splits = static_cast<int>(steps);
-  if (splits < 1) splits = 1;
-  args.rows_per_split = ceil_div64(steps, splits) * kBS;
-  args.splits = splits;
-  if (batch && batch->pool && batch->list.n < kMaxWgradSlots) {
-    const uint64_t need = static_cast<uint64_t>(splits) * chunks * (K + 1) * 128;
-    if (batch->used + need <= batch->pool_floats) {
-      args.partial = batch->pool + batch->used;
-      batch->used += need;
-      WgradReduceSlot& sl = batch->list.s[batch->list.n++];
-      memset(&sl, 0, sizeof(sl));
-      sl.partial = args.partial;
-      sl.dW = dW; sl.lddw = lddw; sl.dW_hi = dW_hi; sl.lddw_hi = lddw_hi; sl.db = db;
-      sl.splits = splits; sl.chunks = chunks; sl.K = K; sl.n_seg = n_seg;
-      for (int i = 0; i < n_seg; ++i) {
-        sl.seg_src[i] = seg_src_host[i]; sl.seg_len[i] = seg_len_host[i]; sl.seg_dst[i] = seg_dst_host[i];
-      }
-      sl.block_begin = batch->blocks;
-      batch->blocks += chunks * (K + 1);
-    }
+  if (batch && batch->pool && batch->defer) {
+    // grouped mode: the problem is queued; wgrad_reduce() launches the whole group, then the reduction
+    WgradArgs probe;
+    UPNERF_TRY(fill_args(&probe, q));       // validate now, where the caller can be named
+    if (batch->n_pending == kMaxWgradSlots) UPNERF_TRY(wgrad_flush(batch, as_stream(stream)));
+    batch->pending[batch->n_pending++] = q;
+    return UPNERF_OK;
   }
+  return launch_group(&q, 1, batch, as_stream(stream));
+}
 
-  CUtensorMap tmY, tmX;
-  UPNERF_TRY(make_tmap_bf16_2d(&tmY, dY, M, N, lddy, kBS, 64));
-  UPNERF_TRY(make_tmap_bf16_2d(&tmX, X, M, K, ldx, kBS, 64));
-  static bool attr_set = false;
-  if (!attr_set) {
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytes));
-    attr_set = true;
-  }
-  dim3 grid(chunks, splits);
-  LaunchScope scope(kCatWgradTc, as_stream(stream), 2.0 * M * N * K, 2.0 * M * (N + K) + 4.0 * N * K);
-  wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmY, tmX, args);
-  UPNERF_CHECK_LAUNCH("wgrad_tc_kernel");
-  return UPNERF_OK;
+// Launches the queued problems of a deferring batch as one group (their partials stay parked in the pool).
+int upnerf::wgrad_flush(WgradBatch* batch, cudaStream_t st) {
+  if (!batch || batch->n_pending == 0) return UPNERF_OK;
+  const int n = batch->n_pending;
+  batch->n_pending = 0;
+  return launch_group(batch->pending, n, batch, st);
 }
 
 uint64_t upnerf::wgrad_pool_floats() {
@@ -392,7 +488,9 @@ uint64_t upnerf::wgrad_pool_floats() {
 }
 
 int upnerf::wgrad_reduce(WgradBatch* batch, cudaStream_t st) {
-  if (!batch || batch->list.n == 0) return UPNERF_OK;
+  if (!batch) return UPNERF_OK;
+  UPNERF_TRY(wgrad_flush(batch, st));
+  if (batch->list.n == 0) return UPNERF_OK;
   {
     LaunchScope scope(kCatWgradReduce, st, 0.0, 0.0);
     wgrad_reduce_kernel<<<batch->blocks, 128, 0, st>>>(batch->list);
