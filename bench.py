@@ -425,6 +425,7 @@ def run_train(args):
 
     if rank != 0:
         if world > 1:
+            system.release_graphs()
             dist.destroy_process_group()
         return
     pk = peaks()
@@ -487,8 +488,9 @@ def run_train(args):
                                            "sample": f"{R} rays/step x 5 timed steps (+2 warm-up), same train step, loss read per step"}
         except Exception as e:          # never lose the bench line to the auxiliary baseline
             line["cuda_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        system.release_graphs()
         dist.destroy_process_group()
 
 
@@ -558,6 +560,7 @@ def run_render(args):
         lib.upnerf_profile_enable(0)
     if rank != 0:
         if world > 1:
+            system.release_graphs()
             dist.destroy_process_group()
         return
     pk = peaks()
@@ -589,8 +592,9 @@ def run_render(args):
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": f"4096-ray chunk x 4 timed (+1 warm-up) of the same no-grad render (oracle port, "
                                           f"{threads} torch threads, flush-denormal on), {sec:.2f} s/chunk"}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
+        system.release_graphs()
         dist.destroy_process_group()
 
 

@@ -81,3 +81,48 @@ def test_two_rank_gradients_equal_concatenated_batch(cuda_dev, tmp_path, precisi
         err = float((outs[0][k].double() - ref).norm() / ref.norm())
         print(f"[{precision}] {k}: 2-rank mean vs concatenated batch, relative {err:.2e}")
         assert err <= tol, (k, err)
+
+
+def _worker_steps(rank, world, port, out_dir, graphed, n_steps):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        sys_ = _system(dev, "bf16")
+        sys_.hparams["kernel.cuda_graph"] = graphed
+        sys_.hparams["nerf.perturb"] = 0.0          # deterministic sampling: the runs are comparable step by step
+        n = R // world
+        losses = []
+        for it in range(n_steps):
+            b = synth.ray_batch(R, N_IMG, 500 + it)
+            b = {k: v[rank * n:(rank + 1) * n].contiguous().to(dev) for k, v in b.items()}
+            losses.append(float(sys_.training_step(b, it)))
+        torch.cuda.synchronize()
+        torch.save({"p_main": sys_.group_main.flat.data.cpu(), "p_pose": sys_.group_pose.flat.data.cpu(),
+                    "losses": losses, "replays": sys_.graph_replays},
+                   os.path.join(out_dir, f"{'g' if graphed else 'e'}{rank}.pt"))
+        sys_.release_graphs()       # before the communicator goes away (see NeRFSystem.release_graphs)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_graphed_steps(cuda_dev, tmp_path):
+    """The step as a CUDA-graph replay WITH its two NCCL all-reduces captured (the fine network's slice goes out
+    between the two backward passes): replicas stay bit-identical without a broadcast, and the losses follow the
+    eagerly launched 2-rank run."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    world, n_steps = 2, 8
+    for graphed in (False, True):
+        mp.spawn(_worker_steps, args=(world, _free_port(), str(tmp_path), graphed, n_steps), nprocs=world, join=True)
+    e = [torch.load(tmp_path / f"e{r}.pt") for r in range(world)]
+    g = [torch.load(tmp_path / f"g{r}.pt") for r in range(world)]
+    assert g[0]["replays"] == n_steps - 3 and e[0]["replays"] == 0
+    for k in ("p_main", "p_pose"):
+        assert torch.equal(g[0][k], g[1][k]), k              # graphed replicas identical
+        assert torch.equal(e[0][k], e[1][k]), k
+    for r in range(world):
+        for i, (a, b) in enumerate(zip(e[r]["losses"], g[r]["losses"])):
+            assert abs(a - b) <= 2e-2 * max(1.0, abs(a)), (r, i, a, b)

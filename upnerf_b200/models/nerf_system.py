@@ -58,6 +58,8 @@ def default_hparams() -> dict:
         # `kernel.cuda_graph_warmup` steps run eagerly (lazy initialisation must not happen under capture)
         "kernel.cuda_graph": os.environ.get("UPNERF_CUDA_GRAPH", "1") != "0",
         "kernel.cuda_graph_warmup": 3,
+        # data-parallel runs capture the two NCCL all-reduces of the step into the graph as well
+        "kernel.cuda_graph_ddp": os.environ.get("UPNERF_CUDA_GRAPH_DDP", "1") != "0",
     }
 
 
@@ -439,7 +441,7 @@ class NeRFSystem(nn.Module):
         sched_mult = self.get_schedule_mult(self._progress)
         if (hp["kernel.cuda_graph"] and hp["kernel.fused_tail"] and rng is None and img_idx.is_cuda
                 and self._steps_seen > hp["kernel.cuda_graph_warmup"] and torch.is_grad_enabled()
-                and (not self._ddp_active() or hp.get("kernel.cuda_graph_ddp", False))):
+                and (not self._ddp_active() or hp["kernel.cuda_graph_ddp"])):
             return self._training_step_graphed(batch, sched_mult)
         loss, loss_d, psnr_ = self._step_body(batch, sched_mult, rng=rng)
         for opt in self._optimizers:
@@ -570,6 +572,15 @@ class NeRFSystem(nn.Module):
             return self._finish_step(out[8], loss_d, out[9])
         finally:
             self._in_graph_step = False
+
+    def release_graphs(self):
+        """Drop every captured step.  Data-parallel runs MUST call this before
+        `torch.distributed.destroy_process_group()`: a captured graph holds NCCL's persistent plans, and
+        NCCL's communicator teardown waits for the graphs that reference it."""
+        if self._graphs:
+            torch.cuda.synchronize(self._device)
+        self._graphs.clear()
+        self._graph_pool = None
 
     def _capture_step(self, batch, sched_mult):
         dev = self._device
