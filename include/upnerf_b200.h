@@ -90,6 +90,9 @@ typedef struct upnerf_epilogue {
   const float* head_b;    /* [n_heads] */
   int head_act;           /* 0 none, 1 softplus(beta=1,threshold=20), 2 sigmoid */
   float* head_out;        /* [M, n_heads] */
+  int head_col_begin;     /* the heads read columns [head_col_begin, N) only (a multiple of 64; head_w entries of the
+                             columns before it are ignored): the stacked candidate|rgb layer feeds its rgb row-dots
+                             from the right half of its output */
 } upnerf_epilogue;
 
 /* bf16 in / bf16 out on tcgen05.  Requires K % 64 == 0, N % 64 == 0, N <= 256,

@@ -37,6 +37,7 @@ class Epilogue(C.Structure):
         ("head_b", C.c_void_p),
         ("head_act", C.c_int),
         ("head_out", C.c_void_p),
+        ("head_col_begin", C.c_int),
     ]
 
 

@@ -260,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       for (int ch = first; ch < nchunks; ch += kGroups) {
+        const int nh_here = ch * 64 >= ep.head_col_begin ? nh : 0;   // (warp-uniform) heads skip the columns before
         // the smem box is free once the previous store of this group has been read out (the
         // leader waited for that before issuing the aux load / arriving at the barrier)
         if (has_aux) {
@@ -327,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // (fully unrolled with a predicate so that hacc[] stays in registers)
 #pragma unroll
             for (int h = 0; h < kMaxHeads; ++h) {
-              if (h < nh) {
+              if (h < nh_here) {
                 const float4 w0 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col]);
                 const float4 w1 = *reinterpret_cast<const float4*>(&sVec[(2 + h) * kMaxN + col + 4]);
                 hacc[h] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x +
@@ -430,6 +431,8 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   if (ep) args.ep = *ep;
   UPNERF_REQUIRE(args.ep.n_heads >= 0 && args.ep.n_heads <= kMaxHeads, UPNERF_ERR_BAD_SHAPE,
                  "gemm_bf16: n_heads=%d", args.ep.n_heads);
+  UPNERF_REQUIRE(args.ep.head_col_begin >= 0 && args.ep.head_col_begin % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "gemm_bf16: head_col_begin=%d must be a multiple of 64", args.ep.head_col_begin);
   UPNERF_REQUIRE(args.ep.aux_mode == 0 || args.ep.aux != nullptr, UPNERF_ERR_BAD_SHAPE,
                  "gemm_bf16: aux_mode set without aux");
   UPNERF_REQUIRE(!args.ep.ray_bias || args.ep.rows_per_ray > 0, UPNERF_ERR_BAD_SHAPE,

@@ -145,7 +145,7 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
     for (int e = 0; e < 4; ++e) w2[h][e] = W2[h * 128 + lane * 4 + e];
   float aw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float ab[3] = {0.f, 0.f, 0.f};
-  constexpr int kB = 4;  // samples whose loads are in flight together
+  constexpr int kB = 4;  // samples whose loads are in flight together (8 was slower: 130 vs 92 us per launch)
   for (int64_t r = blockIdx.x * 4ll + warp; r < R; r += gridDim.x * 4ll) {
     float rb[4] = {0.f, 0.f, 0.f, 0.f};
     for (int s0 = 0; s0 < S; s0 += kB) {

@@ -592,6 +592,7 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     e.ray_bias = Bc;
     e.rows_per_ray = S;
     e.n_heads = 3;
+    e.head_col_begin = H;       // (the left half of hw3 is zero: skip it)
     e.head_w = k.hw3;
     e.head_b = prm + L.br2;
     e.head_act = 2;

@@ -275,42 +275,59 @@ wgrad_tc_kernel(const __grid_constant__ WgradGroupParams grp) {
   }
 }
 
-// One block per (slot, 128-row chunk, packed column): thread = output row.  Sums the splits in a
-// fixed order (bit-reproducible) and adds the result to the parameter gradient.
+// One block per (slot, 128-row chunk, tile of 8 packed columns).  Phase 1: thread = output row sums the splits
+// of its 8 columns in a fixed order (bit-reproducible; the partials are column-major, so these reads are
+// full lines).  Phase 2: the 128 x 32 tile goes through shared memory so that the read-modify-write of the
+// parameter gradient is row-major -- a warp covers 8 consecutive columns (one full 32-byte sector) of 4 rows;
+// the strided version touched a sector per ELEMENT and took longer than reading the partials.
+constexpr int kRedCols = 8;
 __global__ void __launch_bounds__(128)
 wgrad_reduce_kernel(const __grid_constant__ WgradReduceList list) {
+  __shared__ float tile[kRedCols][128 + 1];
   int si = 0;
   while (si + 1 < list.n && static_cast<int>(blockIdx.x) >= list.s[si + 1].block_begin) ++si;
   const WgradReduceSlot& s = list.s[si];
+  const int ctiles = (s.K + 1 + kRedCols - 1) / kRedCols;
   const int local = blockIdx.x - s.block_begin;
-  const int chunk = local / (s.K + 1);
-  const int col = local - chunk * (s.K + 1);
+  const int chunk = local / ctiles;
+  const int col0 = (local - chunk * ctiles) * kRedCols;
   const int row = threadIdx.x;
-  float* dst = nullptr;
-  if (col == s.K) {
-    if (s.db) dst = s.db + chunk * 128 + row;
-  } else {
-    int d = -1;
+  const int ncols = s.K + 1 - col0 < kRedCols ? s.K + 1 - col0 : kRedCols;
+  const int64_t stride = static_cast<int64_t>(s.chunks) * (s.K + 1) * 128;
+  const float* p0 = s.partial + (static_cast<int64_t>(chunk) * (s.K + 1) + col0) * 128 + row;
+  for (int c = 0; c < ncols; ++c) {
+    const float* p = p0 + c * 128;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int i = 0;
+    for (; i + 8 <= s.splits; i += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcs(p + (i + j) * stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j & 3] += v[j];
+    }
+    for (; i < s.splits; ++i) acc[i & 3] += __ldcs(p + i * stride);
+    tile[c][row] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  __syncthreads();
+  const int cidx = threadIdx.x & (kRedCols - 1), r0 = threadIdx.x / kRedCols;   // 16 rows per sweep
+  // destination column of this thread's packed column (or -1: padding), and the bias column K
+  const int col = col0 + cidx;
+  int d = -1;
+  if (cidx < ncols && col < s.K)
     for (int i = 0; i < s.n_seg; ++i)
       if (col >= s.seg_src[i] && col < s.seg_src[i] + s.seg_len[i]) d = s.seg_dst[i] + (col - s.seg_src[i]);
-    if (d >= 0)
-      dst = (chunk == 1 && s.dW_hi) ? s.dW_hi + static_cast<int64_t>(row) * s.lddw_hi + d
-                                    : s.dW + static_cast<int64_t>(chunk * 128 + row) * s.lddw + d;
+  const bool is_bias = cidx < ncols && col == s.K;
+  for (int r = r0; r < 128; r += 128 / kRedCols) {
+    const float v = tile[cidx][r];
+    if (d >= 0) {
+      float* dst = (chunk == 1 && s.dW_hi) ? s.dW_hi + static_cast<int64_t>(r) * s.lddw_hi + d
+                                           : s.dW + static_cast<int64_t>(chunk * 128 + r) * s.lddw + d;
+      *dst += v;
+    } else if (is_bias && s.db) {
+      s.db[chunk * 128 + r] += v;
+    }
   }
-  if (!dst) return;
-  const int64_t stride = static_cast<int64_t>(s.chunks) * (s.K + 1) * 128;
-  const float* p = s.partial + (static_cast<int64_t>(chunk) * (s.K + 1) + col) * 128 + row;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int i = 0;
-  for (; i + 8 <= s.splits; i += 8) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldcs(p + (i + j) * stride);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j & 3] += v[j];
-  }
-  for (; i < s.splits; ++i) acc[i & 3] += __ldcs(p + i * stride);
-  *dst += (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 }  // namespace
@@ -425,7 +442,7 @@ int launch_group(const WgradProblem* probs, int n, WgradBatch* batch, cudaStream
           sl.seg_src[j] = q.seg_src[j]; sl.seg_len[j] = q.seg_len[j]; sl.seg_dst[j] = q.seg_dst[j];
         }
         sl.block_begin = batch->blocks;
-        batch->blocks += a.chunks * (q.K + 1);
+        batch->blocks += a.chunks * ((q.K + 1 + kRedCols - 1) / kRedCols);
       }
     }
     UPNERF_TRY(make_tmap_bf16_2d(&g->tmY[i], q.dY, q.M, q.N, q.lddy, kBS, 64));
