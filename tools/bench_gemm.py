@@ -28,6 +28,32 @@ def main():
         if a.startswith("M="):
             M = int(a[2:])
     only_trunk = "trunk" in sys.argv[1:]
+    if "epi" in sys.argv[1:]:       # which epilogue feature costs what (the head layers of the render forward)
+        Mm, S = 4096 * 128, 128
+        for (N, K) in [(256, 256), (128, 128)]:
+            A = torch.randn(Mm, 256, device=dev).bfloat16()[:, :K]
+            B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+            Cc = torch.empty(Mm, 256, device=dev, dtype=torch.bfloat16)[:, :N]
+            bias = torch.randn(N, device=dev)
+            rb = torch.randn(Mm // S, N, device=dev)
+            hw = torch.randn(3, N, device=dev)
+            hb = torch.zeros(3, device=dev)
+            ho = torch.empty(Mm, 3, device=dev)
+            variants = {
+                "bias+relu": dict(bias=bias, act=1),
+                "ray_bias+relu": dict(ray_bias=rb, rows_per_ray=S, act=1),
+                "bias+relu+3 heads": dict(bias=bias, act=1, head_w=hw, head_b=hb, head_act=2, head_out=ho),
+                "ray_bias+relu+3 heads": dict(ray_bias=rb, rows_per_ray=S, act=1, head_w=hw, head_b=hb, head_act=2, head_out=ho),
+                "ray_bias+relu+1 head": dict(ray_bias=rb, rows_per_ray=S, act=1, head_w=hw[:1].contiguous(), head_b=hb, head_act=1, head_out=ho),
+            }
+            for name, kw in variants.items():
+                ep = L.make_epilogue(**kw)
+                if "3 heads" in name and N == 256:
+                    ep.head_col_begin = 128
+                ms = timeit(lambda: L.gemm_bf16(A, B, Cc, Mm, N, K, ep=ep), iters=20)
+                by = (Mm * K + Mm * N) * 2
+                print(f"gemm_bf16 M={Mm} N={N} K={K} lda={A.stride(0)} {name:24s}: {ms * 1e3:7.1f} us  {by / ms / 1e6:6.0f} GB/s")
+        return
     if "tf32" in sys.argv[1:]:      # the small per-ray / parameter-space products (render.cu), one launch each
         R = 4096
         for name, (Mm, Nn, Kk), sa, sb, split, acc in [

@@ -243,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t crow = row_ok ? grow : (args.M - 1);
       const float r1 = ep.rank1_row ? ep.rank1_row[crow] : 0.f;
       const float* rb = ep.ray_bias ? ep.ray_bias + (crow / ep.rows_per_ray) * N : nullptr;
+      const bool rb_uniform = rb && (ep.rows_per_ray % 32 == 0);
       float hacc[kMaxHeads] = {0.f, 0.f, 0.f};
       prefetch_ray_bias(t + 1);
 
@@ -261,6 +262,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       for (int ch = first; ch < nchunks; ch += kGroups) {
         const int nh_here = ch * 64 >= ep.head_col_begin ? nh : 0;   // (warp-uniform) heads skip the columns before
+        // Per-ray bias of this box.  A warp's 32 rows start at a multiple of 32, so with rows_per_ray % 32 == 0
+        // they all belong to ONE ray: each lane fetches two of the box's 64 columns now (one coalesced 256-byte
+        // read, in flight across the barrier and the TMEM load below) and the values reach the rows by shuffle.
+        // (Sixteen dependent 16-byte loads per thread and box -- L1 hits or not -- were 42 % of this kernel's
+        // stall samples on the stacked candidate|rgb layer.)
+        float2 rbv = make_float2(0.f, 0.f);
+        if (rb_uniform) rbv = __ldg(reinterpret_cast<const float2*>(rb + ch * 64) + lane);
         // the smem box is free once the previous store of this group has been read out (the
         // leader waited for that before issuing the aux load / arriving at the barrier)
         if (has_aux) {
@@ -285,11 +293,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc_r[c4 * 8 + e]);
             const int col = ch * 64 + c8 * 8;
-            const float4 b0 = *reinterpret_cast<const float4*>(&sVec[col]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&sVec[col + 4]);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            if (rb) {
+            if (ep.bias) {      // (layers whose bias rides in the per-ray bias pass none: no loads at all)
+              const float4 b0 = *reinterpret_cast<const float4*>(&sVec[col]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&sVec[col + 4]);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (rb_uniform) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += __shfl_sync(0xffffffffu, rbv.x, c8 * 4 + e);
+                v[2 * e + 1] += __shfl_sync(0xffffffffu, rbv.y, c8 * 4 + e);
+              }
+            } else if (rb) {
               const float4 p0 = __ldg(reinterpret_cast<const float4*>(rb + col));
               const float4 p1 = __ldg(reinterpret_cast<const float4*>(rb + col + 4));
               v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
@@ -378,21 +394,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 
       if (nh > 0) {
-        // row-dot heads: partial sums of the groups are combined by group 0
-        float* slot = sHead + ((acc * kGroups + grp) * kBM + row_in_tile) * kMaxHeads;
+        // Row-dot heads: every group that owned a chunk at or after head_col_begin holds a partial sum per row;
+        // one group combines them.  Where possible only the contributing groups meet at the named barrier (a
+        // barrier over all 512 epilogue threads per tile keeps the groups in lock step and cost the
+        // 128-wide layers 20 % of their time); with 2 chunks per tile the set alternates between {0,1} and {2,3}
+        // -- one barrier id per parity.
+        const int c0 = ep.head_col_begin >> 6;
+        const int ncontrib = nchunks - c0;
+        // (With 4 chunks per tile everybody meets and group 0 -- whose own box carries no head columns in the
+        //  stacked layer -- combines: making a contributing group combine as well measured 27 us SLOWER there,
+        //  it becomes the critical group.  With 2 chunks per tile the two idle groups skip the barrier: -16 us.)
+        const bool regular = nchunks == 2 || (ncontrib == 1 && nchunks <= 2);
+        const bool mine = regular ? (first >= c0 && first < nchunks) : true;
+        const int comb_grp = regular ? ((c0 + t * nchunks) & (kGroups - 1)) : 0;
+        // exchange buffer: a slot is rewritten two uses of the same group set later, i.e. after a barrier the
+        // combiner of the earlier tile has passed too (sets alternate tile by tile when nchunks == 2)
+        const int hb = nchunks == 2 ? ((t >> 1) & 1) : (t & 1);
+        if (mine) {
+          float* slot = sHead + ((hb * kGroups + grp) * kBM + row_in_tile) * kMaxHeads;
 #pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h)
-          if (h < nh) slot[h] = hacc[h];
-        named_bar_sync(6, kEpiThreads);
-        if (grp == 0 && row_ok) {
-          for (int h = 0; h < nh; ++h) {
-            float x = ep.head_b[h];
+          for (int h = 0; h < kMaxHeads; ++h)
+            if (h < nh) slot[h] = hacc[h];
+          if (!regular) named_bar_sync(6, kEpiThreads);
+          else if (ncontrib > 1) named_bar_sync(6 + (nchunks == 2 ? (t & 1) : 0), 128 * ncontrib);
+          if (grp == comb_grp && row_ok) {
+            for (int h = 0; h < nh; ++h) {
+              float x = ep.head_b[h];
+              if (regular) {
+                for (int j = 0; j < ncontrib; ++j)
+                  x += sHead[((hb * kGroups + ((c0 + j + t * nchunks) & (kGroups - 1))) * kBM + row_in_tile) * kMaxHeads + h];
+              } else {
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g)
-              x += sHead[((acc * kGroups + g) * kBM + row_in_tile) * kMaxHeads + h];
-            if (ep.head_act == 1) x = softplus_ref(x);
-            else if (ep.head_act == 2) x = sigmoid_ref(x);
-            ep.head_out[grow * nh + h] = x;
+                for (int g = 0; g < kGroups; ++g)
+                  x += sHead[((hb * kGroups + g) * kBM + row_in_tile) * kMaxHeads + h];
+              }
+              if (ep.head_act == 1) x = softplus_ref(x);
+              else if (ep.head_act == 2) x = sigmoid_ref(x);
+              ep.head_out[grow * nh + h] = x;
+            }
           }
         }
       }

@@ -468,6 +468,8 @@ int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, cons
   if (ph.rgb) {
     if (cfg.encode_feat) {
       // Wq = W_rgb0[:, :F] W_sf  (128 x 256);  bq_const = W_rgb0[:, :F] b_sf + b_rgb0
+      // (not split over K: atomics would make the folded weights -- and with them every forward output --
+      //  differ in the last bits from call to call)
       UPNERF_TRY(mm(cl, prm + L.Wr0, L.rgb_in, 1, prm + L.Wsf, 1, W, k.Wq32, W, 1, H, W, L.F, nullptr, 0));
       upnerf_epilogue e = ep_none();
       e.bias = prm + L.br0;
