@@ -91,3 +91,40 @@ def test_graphed_step_launch_accounting(cuda_dev):
     assert sys_.graph_replays == 3
     assert counts[3] >= counts[4] == counts[5] > 50, counts  # step 4 also counted the launches under capture
     assert abs(counts[5] - counts[2]) <= 2, counts            # eager and replayed steps launch the same kernels
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_graphed_inference_chunks_equal_eager(cuda_dev, precision):
+    """Chunked no-grad render (NeRFSystem.forward(train=False), models/nerf_system.py:104-126): full chunks replayed
+    from one captured graph + an eager ragged tail must reproduce the eagerly launched chunks bit for bit -- also
+    after the parameters have moved (the graph reads them live)."""
+    from upnerf_b200.utils import ray as ray_utils
+
+    n_img, chunk = 12, 256
+    sys_, _, _ = make_system(n_img, 32, 32, precision, 1000, cuda_dev)
+    sys_.set_progress(0.75)
+    sys_.hparams["val.chunk_size"] = chunk
+    B = 3 * chunk + 100
+    b = {k: v.to(cuda_dev) for k, v in synth.ray_batch(B, n_img, 77).items()}
+
+    def render(graphed):
+        sys_.hparams["kernel.cuda_graph"] = graphed
+        with torch.no_grad():
+            o, d = ray_utils.get_rays(b["directions"], b["c2w"])
+            rays = torch.cat([o, d, b["ray_infos"]], 1)
+            return sys_(rays, b["feats"], b["img_idx"], 1.0, train=False)
+
+    ref = render(False)
+    r0 = sys_.graph_replays
+    got = render(True)
+    assert sys_.graph_replays == r0 + 3
+    assert set(ref) == set(got)
+    for k in ref:
+        assert ref[k].shape == got[k].shape and torch.equal(ref[k], got[k]), k
+    with torch.no_grad():                      # parameters move: the replays must see the new values
+        sys_.nerf_fine.rgb_share_layer[2].bias.add_(0.25)
+        sys_.embedding_fine_a.weight.mul_(1.5)
+    ref2, got2 = render(False), render(True)
+    assert not torch.equal(ref2["rgb_fine"], ref["rgb_fine"])
+    for k in ref2:
+        assert torch.equal(ref2[k], got2[k]), k

@@ -385,21 +385,28 @@ class NeRFSystem(nn.Module):
                 t = self.transient_net(feats, img_idx)
             feats.record_stream(side)
             img_idx.record_stream(side)
-        results = defaultdict(list)
-        for i in range(0, B, chunk):
-            part = render_rays(models=self.models, embeddings=self.embeddings, rays=rays[i:i + chunk],
-                               img_idx=img_idx[i:i + chunk], sched_mult=sched_mult,
-                               sched_phase=0 if sched_mult == 0 else (2 if sched_mult == 1 else 1),
-                               N_samples=hp["nerf.N_samples"], use_disp=hp["nerf.use_disp"],
-                               perturb=hp["nerf.perturb"] if train else 0, N_importance=hp["nerf.N_importance"],
-                               white_back=self.white_back, encode_feat=hp["nerf.feat_dim"] > 0,
-                               validation=not train, precision=hp["kernel.precision"], rng=rng,
-                               grad_sink=self._grad_sinks if (train and B == chunk) else None,
-                               after_fine_bwd=self._reduce_fine_async if (train and B == chunk and self._ddp_active())
-                               else None)
-            for k, v in part.items():
-                results[k].append(v)
-        results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
+        kw = dict(models=self.models, embeddings=self.embeddings, sched_mult=sched_mult,
+                  sched_phase=0 if sched_mult == 0 else (2 if sched_mult == 1 else 1),
+                  N_samples=hp["nerf.N_samples"], use_disp=hp["nerf.use_disp"],
+                  perturb=hp["nerf.perturb"] if train else 0, N_importance=hp["nerf.N_importance"],
+                  white_back=self.white_back, encode_feat=hp["nerf.feat_dim"] > 0,
+                  validation=not train, precision=hp["kernel.precision"])
+        if (not train and hp["kernel.cuda_graph"] and rays.is_cuda and not torch.is_grad_enabled() and rng is None
+                and B >= 2 * chunk):
+            # inference (config 5: a 1920x1080 image is 507 chunks of val.chunk_size rays): one captured chunk,
+            # replayed per chunk -- the eager per-chunk host work (30 launches through Python) took longer than
+            # the chunk's 1.2 ms on the device
+            results = self._render_chunks_graphed(rays, img_idx, chunk, kw)
+        else:
+            results = defaultdict(list)
+            for i in range(0, B, chunk):
+                part = render_rays(rays=rays[i:i + chunk], img_idx=img_idx[i:i + chunk], rng=rng,
+                                   grad_sink=self._grad_sinks if (train and B == chunk) else None,
+                                   after_fine_bwd=self._reduce_fine_async if (train and B == chunk and self._ddp_active())
+                                   else None, **kw)
+                for k, v in part.items():
+                    results[k].append(v)
+            results = {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in results.items()}
         if sched_mult > 0:
             if t is None:
                 t = self.transient_net(feats, img_idx)
@@ -572,6 +579,48 @@ class NeRFSystem(nn.Module):
             return self._finish_step(out[8], loss_d, out[9])
         finally:
             self._in_graph_step = False
+
+    def _render_chunks_graphed(self, rays, img_idx, chunk, kw):
+        """Chunked no-grad render (models/nerf_system.py:104-126) with the full chunks replayed from ONE captured
+        graph: static input buffers, outputs copied into preallocated full-size tensors.  The captured kernels
+        read parameters, `progress` and embeddings from their live buffers, so training may continue between
+        renders; everything baked into the graph is part of its key."""
+        B = rays.shape[0]
+        key = ("render", chunk, float(kw["sched_mult"]), kw["N_samples"], kw["N_importance"], bool(kw["use_disp"]),
+               kw["precision"], rays.dtype, img_idx.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            s_rays = rays[:chunk].contiguous().clone()
+            s_idx = img_idx[:chunk].contiguous().clone()
+            render_rays(rays=s_rays, img_idx=s_idx, **kw)          # lazy initialisation outside the capture
+            torch.cuda.synchronize(rays.device)
+            graph = torch.cuda.CUDAGraph()
+            launches0 = _L.launch_count()
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                part = render_rays(rays=s_rays, img_idx=s_idx, **kw)
+            g = {"graph": graph, "rays": s_rays, "idx": s_idx, "part": part, "launches": _L.launch_count() - launches0}
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g
+        out = {k: torch.empty((B,) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype) for k, v in g["part"].items()}
+        n_full = B // chunk
+        for c in range(n_full):
+            i = c * chunk
+            g["rays"].copy_(rays[i:i + chunk], non_blocking=True)
+            g["idx"].copy_(img_idx[i:i + chunk], non_blocking=True)
+            g["graph"].replay()
+            _L.launch_count_add(g["launches"])
+            self.graph_replays += 1
+            for k, v in g["part"].items():
+                out[k][i:i + chunk].copy_(v, non_blocking=True)
+        if n_full * chunk < B:                                      # the ragged last chunk runs eagerly
+            i = n_full * chunk
+            part = render_rays(rays=rays[i:], img_idx=img_idx[i:], **kw)
+            for k, v in part.items():
+                out[k][i:].copy_(v)
+        return out
 
     def release_graphs(self):
         """Drop every captured step.  Data-parallel runs MUST call this before
