@@ -301,13 +301,14 @@ struct Ctx {
   // so it runs beside the tensor-core chain instead of inside it.  side == st when disabled.
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pro[2] = {nullptr, nullptr};   // side stream: head operands + per-ray biases of pass 0 / 1 are ready
   Ctx leaf() const { Ctx c = *this; c.st = side; c.wb = nullptr; return c; }
   bool has_side() const { return side != st; }
 };
 
 // One side stream and one fork/join event pair per device, created on first use and kept for the
 // life of the process (UPNERF_SIDE_STREAM=0 disables the overlap: everything stays on one stream).
-struct SideRes { cudaStream_t st; cudaEvent_t fork_ev, join_ev; int state; };
+struct SideRes { cudaStream_t st; cudaEvent_t fork_ev, join_ev, pro_ev[2]; int state; };
 SideRes* side_res() {
   static SideRes res[32];
   static int enabled = -1;
@@ -323,7 +324,9 @@ SideRes* side_res() {
     r.state = -1;
     if (cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking) == cudaSuccess &&
         cudaEventCreateWithFlags(&r.fork_ev, cudaEventDisableTiming) == cudaSuccess &&
-        cudaEventCreateWithFlags(&r.join_ev, cudaEventDisableTiming) == cudaSuccess)
+        cudaEventCreateWithFlags(&r.join_ev, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&r.pro_ev[0], cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&r.pro_ev[1], cudaEventDisableTiming) == cudaSuccess)
       r.state = 1;
   }
   return r.state == 1 ? &r : nullptr;
@@ -332,7 +335,10 @@ Ctx make_ctx(int dtype, size_t es, cudaStream_t st, WgradBatch* wb) {
   Ctx c;
   c.dtype = dtype; c.es = es; c.st = st; c.wb = wb;
   c.side = st;
-  if (SideRes* r = side_res()) { c.side = r->st; c.ev_fork = r->fork_ev; c.ev_join = r->join_ev; }
+  if (SideRes* r = side_res()) {
+    c.side = r->st; c.ev_fork = r->fork_ev; c.ev_join = r->join_ev;
+    c.ev_pro[0] = r->pro_ev[0]; c.ev_pro[1] = r->pro_ev[1];
+  }
   return c;
 }
 // side stream picks up everything launched on the main stream so far
@@ -487,12 +493,16 @@ int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, cons
 }
 
 // ------------------------------------------------------------------ one network, forward
-int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
-             const upnerf_pass_io& io, PassBufs& p) {
+// Everything of a pass that depends on parameters, rays and embeddings only -- not on the sample depths: packed
+// GEMM operands (trunk on the main stream, heads on the side stream) and the per-ray biases of the head layers.
+// The render forward issues the prologues of BOTH passes up front: the fine pass's side-stream chain (~100 us of
+// small kernels that cannot share an SM with the tensor-core kernels) then runs in the TMEM-free window between
+// the coarse head layers and the fine trunk instead of holding up the fine head layers.
+int pass_prologue(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
+                  const upnerf_pass_io& io, PassBufs& p, int which) {
   const upnerf_net_config& cfg = a.cfg;
   const float* prm = io.params;
-  const int64_t M = p.M, R = p.R;
-  const int S = p.S;
+  const int64_t R = p.R;
   Packed& k = p.pk;
   const Ctx cl = c.leaf();
   UPNERF_TRY(pack_weights(c, cl, cfg, L, ph, prm, k));   // forks the side stream
@@ -531,6 +541,25 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
     UPNERF_CHECK_CUDA(cudaMemcpy2DAsync(k.hw3 + H, H2 * sizeof(float), prm + L.Wr2, H * sizeof(float),
                                         H * sizeof(float), 3, cudaMemcpyDeviceToDevice, cl.st));
   }
+
+  if (c.has_side()) UPNERF_CHECK_CUDA(cudaEventRecord(c.ev_pro[which], c.side));
+  return UPNERF_OK;
+}
+
+// ------------------------------------------------------------------ one network, forward (after its prologue)
+int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, const Phase& ph,
+             const upnerf_pass_io& io, PassBufs& p, int which) {
+  const upnerf_net_config& cfg = a.cfg;
+  const float* prm = io.params;
+  const int64_t M = p.M, R = p.R;
+  const int S = p.S;
+  Packed& k = p.pk;
+  const Ctx cl = c.leaf();
+  const int H2 = 2 * H;
+  const bool stack = ph.cand && ph.rgb && c.dtype == UPNERF_BF16;
+  float* Bc = p.Bc;
+  float* Bq = stack ? p.Bc + H : p.Bq;
+  upnerf_epilogue e = ep_none();
 
   // positional encoding of x = o + d z straight into the skip buffer [H4 | PE]
   void* PE = col(p.X4, W, c.es);
@@ -586,8 +615,8 @@ int pass_fwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
 
   // Head layers on HF.  candidate_encoding.0 and (folded) rgb_share_layer.0 read the same input, so
   // with both live (phase 1) they run as ONE stacked 256-wide GEMM into the side-by-side buffer
-  // [G1 | Q]; the per-ray biases and head operands come from the side stream.
-  UPNERF_TRY(join_side(c));
+  // [G1 | Q]; the per-ray biases and head operands come from the side stream (this pass's prologue).
+  if (c.has_side()) UPNERF_CHECK_CUDA(cudaStreamWaitEvent(c.st, c.ev_pro[which], 0));
   if (stack) {
     e = ep_none();
     e.act = 1;
@@ -945,7 +974,9 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
   UPNERF_TRY(upnerf_stratified_z(a->rays, a->perturb_rand, a->perturb, a->use_disp, R, S, pl.coarse.z, c.st));
   if (a->z_coarse)
     UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_coarse, pl.coarse.z, R * S * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
-  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->coarse, pl.coarse));
+  UPNERF_TRY(pass_prologue(c, *a, pl.L, ph, a->coarse, pl.coarse, 0));
+  if (a->n_importance > 0) UPNERF_TRY(pass_prologue(c, *a, pl.L, ph, a->fine, pl.fine, 1));
+  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->coarse, pl.coarse, 0));
   if (a->n_importance == 0) return join_side(c);
 
   // hierarchical resampling (models/rendering.py:262-307)
@@ -969,7 +1000,7 @@ int upnerf_render_fwd(const upnerf_render_args* a, void* stream) {
                                    1e-5f, pl.fine.z, c.st));
   if (a->z_fine)
     UPNERF_CHECK_CUDA(cudaMemcpyAsync(a->z_fine, pl.fine.z, R * pl.S_f * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
-  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->fine, pl.fine));
+  UPNERF_TRY(pass_fwd(c, *a, pl.L, ph, a->fine, pl.fine, 1));
   return join_side(c);
 }
 
