@@ -148,34 +148,47 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
   constexpr int kB = 4;  // samples whose loads are in flight together (8 was slower: 130 vs 92 us per launch)
   for (int64_t r = blockIdx.x * 4ll + warp; r < R; r += gridDim.x * 4ll) {
     float rb[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int s0 = 0; s0 < S; s0 += kB) {
-      float qv[kB][4], g[kB][3];
-#pragma unroll
-      for (int j = 0; j < kB; ++j) {
-        const int64_t m = r * S + min(s0 + j, S - 1);
-        ld4(Q + m * ldq + lane * 4, qv[j]);
+    for (int sb = 0; sb < S; sb += 32) {
+      // g = d_rgb * rgb (1 - rgb) of 32 samples at once: lane j owns sample sb + j (two coalesced 384-byte reads
+      // instead of six broadcast loads per sample and lane: the kernel was LSU-issue bound), shuffled to the
+      // warp sample by sample below
+      float gl[3] = {0.f, 0.f, 0.f};
+      if (sb + lane < S) {
+        const int64_t m = r * S + sb + lane;
 #pragma unroll
         for (int h = 0; h < 3; ++h) {
           const float y = __ldg(rgb + m * 3 + h);
-          g[j][h] = __ldg(d_rgb + m * 3 + h) * y * (1.f - y);
+          gl[h] = __ldg(d_rgb + m * 3 + h) * y * (1.f - y);
         }
       }
 #pragma unroll
-      for (int j = 0; j < kB; ++j) {
-        if (s0 + j >= S) break;
-        const int64_t m = r * S + s0 + j;
-        float d[4];
+      for (int h = 0; h < 3; ++h) ab[h] += gl[h];       // (summed over lanes at the end)
+      const int nb = S - sb < 32 ? S - sb : 32;
+      for (int s0 = 0; s0 < nb; s0 += kB) {
+        float qv[kB][4];
 #pragma unroll
-        for (int h = 0; h < 3; ++h) ab[h] += g[j][h];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          d[e] = qv[j][e] > 0.f ? (g[j][0] * w2[0][e] + g[j][1] * w2[1][e] + g[j][2] * w2[2][e]) : 0.f;
-          rb[e] += d[e];
-          aw[0][e] += g[j][0] * qv[j][e];
-          aw[1][e] += g[j][1] * qv[j][e];
-          aw[2][e] += g[j][2] * qv[j][e];
+        for (int j = 0; j < kB; ++j) {
+          const int64_t m = r * S + sb + min(s0 + j, nb - 1);
+          ld4(Q + m * ldq + lane * 4, qv[j]);
         }
-        st4(dQ + m * lddq + lane * 4, d);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+          if (s0 + j >= nb) break;
+          const int64_t m = r * S + sb + s0 + j;
+          const float g0 = __shfl_sync(0xffffffffu, gl[0], s0 + j);
+          const float g1 = __shfl_sync(0xffffffffu, gl[1], s0 + j);
+          const float g2 = __shfl_sync(0xffffffffu, gl[2], s0 + j);
+          float d[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            d[e] = qv[j][e] > 0.f ? (g0 * w2[0][e] + g1 * w2[1][e] + g2 * w2[2][e]) : 0.f;
+            rb[e] += d[e];
+            aw[0][e] += g0 * qv[j][e];
+            aw[1][e] += g1 * qv[j][e];
+            aw[2][e] += g2 * qv[j][e];
+          }
+          st4(dQ + m * lddq + lane * 4, d);
+        }
       }
     }
     float* o = d_raybias + r * 128 + lane * 4;
@@ -186,6 +199,10 @@ rgb_head_bwd_kernel(const T* __restrict__ Q, int64_t ldq, const float* __restric
   for (int h = 0; h < 3; ++h)
 #pragma unroll
     for (int e = 0; e < 4; ++e) red[warp][h * 128 + lane * 4 + e] = aw[h][e];
+#pragma unroll
+  for (int h = 0; h < 3; ++h)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ab[h] += __shfl_xor_sync(0xffffffffu, ab[h], o);
   if (lane == 0) {
     red[warp][384] = ab[0];
     red[warp][385] = ab[1];
