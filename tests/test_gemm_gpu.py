@@ -203,7 +203,7 @@ def _trunk_reference(pe, ws, bs, sw, sb):
     return outs, sig
 
 
-@pytest.mark.parametrize("variant", ["dual", "multicast", "2sm"])
+@pytest.mark.parametrize("variant", ["dual", "multicast", "2sm", "multicast-tma-store", "multicast-epilogue-copy"])
 @pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1, 128 * 148 * 5 + 77])
 def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
@@ -214,6 +214,8 @@ def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
 
     monkeypatch.setenv("UPNERF_TRUNK_DUAL", "1" if variant == "dual" else "0")
     monkeypatch.setenv("UPNERF_TRUNK_2SM", "1" if variant == "2sm" else "0")
+    # activation store path of the default kernel: 2 = copy-out warps (default), 0 = TMA stores, 1 = epilogue copy
+    monkeypatch.setenv("UPNERF_TRUNK_LSU_STORE", {"multicast-tma-store": "0", "multicast-epilogue-copy": "1"}.get(variant, "2"))
 
     g = torch.Generator(device="cpu").manual_seed(M)
     pe = _bf16(torch.randn(M, 64, generator=g))
@@ -243,13 +245,17 @@ def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     assert torch.allclose(sig, ref_sig, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("store", ["0", "1", "2"])
 @pytest.mark.parametrize("M", [128 * 2 + 77, 128 * 148 * 2 + 128 * 3 + 9])
-def test_mlp_trunk_bwd_fused(cuda_dev, M):
+def test_mlp_trunk_bwd_fused(cuda_dev, M, store, monkeypatch):
     """Fused backward chain: dY8 = (dHF W_F + dssig (x) w_s) * [H8>0], dYl = (dY(l+1) W(l+1)) * [Hl>0],
     with the ReLU bit masks written by the fused forward, against layer-wise fp32 math on the same
-    bf16 operands (masks taken from the forward kernel's own activations, so no mask can flip)."""
+    bf16 operands (masks taken from the forward kernel's own activations, so no mask can flip); for the three
+    activation store paths of the kernel (UPNERF_TRUNK_BWD_STORE: 0 TMA stores, 1 epilogue copy, 2 copy-out
+    warps = default)."""
     from upnerf_b200 import _lib as L
 
+    monkeypatch.setenv("UPNERF_TRUNK_BWD_STORE", store)
     g = torch.Generator(device="cpu").manual_seed(M + 1)
     d = lambda t: t.to(cuda_dev)
     pe = _bf16(torch.randn(M, 64, generator=g))

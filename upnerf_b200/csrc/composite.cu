@@ -129,7 +129,9 @@ __device__ __forceinline__ Sample load_sample(const CompArgs& p, int64_t r, int 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32) composite_fwd_kernel(const CompArgs p) {
+// (7 blocks per SM: 4096 rays = 1024 blocks fit ONE wave of 148 x 7; at 6 blocks per SM the 136 blocks of a second
+//  wave doubled the kernel's time at the training batch size)
+__global__ void __launch_bounds__(kWarps * 32, 7) composite_fwd_kernel(const CompArgs p) {
   __shared__ float s_ws[kWarps][kMaxS];
   __shared__ float s_wc[kWarps][kMaxS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
