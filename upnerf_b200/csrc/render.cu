@@ -407,6 +407,12 @@ int mm(const Ctx& c, const float* A, int64_t sam, int64_t sak, const float* B, i
     // an accumulating product without an epilogue may as well be split over K (atomics into the existing
     // values): the parameter-space chain rules have 1..3 output tiles and would otherwise run 8 K-chunks in a row
     if (accumulate && !ep && split_k == 1 && K > 32) split_k = static_cast<int>(K / 32 < 8 ? K / 32 : 8);
+    // one CTA per SM: keep tiles x splits within ONE wave (6 tiles x 32 splits = 192 CTAs ran as two)
+    if (split_k > 2) {
+      const int64_t tiles = ceil_div64(M, 128) * ceil_div64(N, 128);
+      const int64_t cap = sm_count() / tiles;
+      if (cap >= 2 && split_k > cap) split_k = static_cast<int>(cap);
+    }
     return upnerf_gemm_tf32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
   }
   return upnerf_gemm_f32(A, sam, sak, B, sbn, sbk, C, scm, scn, M, N, K, ep, accumulate, split_k, c.st);
