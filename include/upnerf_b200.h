@@ -99,6 +99,11 @@ typedef struct upnerf_epilogue {
  * 16-byte aligned pointers and leading dimensions that are multiples of 8. */
 int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                      int64_t M, int N, int K, const upnerf_epilogue* ep, void* stream);
+/* The same layer with its input split over TWO row-major operands along K: C = epi([A1 | A2] B^T), B [N, K1+K2].
+ * One pass instead of two accumulating launches for sums of products over the same rows -- the positional-encoding
+ * gradient dPE = dY5 W5[:, pe] + dY1 W1 (the two layers that read the encoding, models/nerf.py:84-93). */
+int upnerf_gemm2_bf16(const void* A1, int64_t lda1, int K1, const void* A2, int64_t lda2, int K2, const void* B,
+                      int64_t ldb, void* C, int64_t ldc, int64_t M, int N, const upnerf_epilogue* ep, void* stream);
 
 /* Fused trunk forward on tcgen05 (bf16 in, fp32 accumulate, bf16 out): per 128-sample tile
  * PE -> xyz_encoding_1..8 (Linear 256 + ReLU, skip concat [PE | h] at layer 5) ->

@@ -369,3 +369,22 @@ def test_gemm_tf32_strided(cuda_dev, case):
     print(f"{case}: vs tf32-rounded operands {err_t:.2e}, vs exact {err_e:.2e}")
     assert err_t <= 2e-6, err_t          # fp32 accumulation of exact tf32 products
     assert err_e <= 1e-3, err_e          # tf32 operand resolution (2^-11 per operand)
+
+
+@pytest.mark.parametrize("M", [128 * 5 + 3, 128 * 148 * 2 + 77])
+def test_gemm2_bf16_two_operands(cuda_dev, M):
+    """upnerf_gemm2_bf16: C = [A1 | A2] B^T in one pass (the positional-encoding gradient dPE = dY5 W5[:, pe] + dY1 W1)
+    against fp32 math on the same bf16 operands."""
+    from upnerf_b200 import _lib as L
+
+    g = torch.Generator(device="cpu").manual_seed(M)
+    A1 = _bf16(torch.randn(M, 256, generator=g)).to(cuda_dev)
+    A2 = _bf16(torch.randn(M, 256, generator=g)).to(cuda_dev)
+    B = _bf16(torch.randn(64, 512, generator=g) / 16).to(cuda_dev)
+    Cc = torch.full((M, 64), float("nan"), dtype=torch.bfloat16, device=cuda_dev)
+    L.gemm2_bf16(A1, A2, B, Cc, M, 64, 256, 256)
+    torch.cuda.synchronize()
+    ref = A1.float() @ B[:, :256].float().t() + A2.float() @ B[:, 256:].float().t()
+    err = float((Cc.float() - ref).abs().max())
+    assert torch.isfinite(Cc.float()).all()
+    assert err <= 0.02 * max(1.0, float(ref.abs().max())), err

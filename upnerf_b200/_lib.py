@@ -125,6 +125,14 @@ def gemm_bf16(A, B, C_out, M, N, K, lda=None, ldb=None, ldc=None, ep: Epilogue |
     check(st, "upnerf_gemm_bf16")
 
 
+def gemm2_bf16(A1, A2, B, C_out, M, N, K1, K2, ep: Epilogue | None = None):
+    """C[M,N] = epi([A1 | A2] @ B[N,K1+K2]^T) on tcgen05 (see upnerf_gemm2_bf16)."""
+    st = lib().upnerf_gemm2_bf16(ptr(A1), _i64(A1.stride(0)), C.c_int(K1), ptr(A2), _i64(A2.stride(0)), C.c_int(K2),
+                                 ptr(B), _i64(B.stride(0)), ptr(C_out), _i64(C_out.stride(0)), _i64(M), C.c_int(N),
+                                 C.byref(ep) if ep is not None else None, stream_ptr())
+    check(st, "upnerf_gemm2_bf16")
+
+
 def wgrad_bf16(dY, X, dW, db, M, N, K, segs, lddy=None, ldx=None, lddw=None):
     """dW[n, map(k)] += dY^T X, db[n] += colsum(dY) on tcgen05 (see upnerf_wgrad_bf16)."""
     lddy = dY.stride(0) if lddy is None else lddy

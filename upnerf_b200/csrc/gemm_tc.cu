@@ -59,6 +59,7 @@ struct GemmArgs {
   int64_t M;
   int N;
   int K;
+  int kb1;        // K-blocks (of 64) taken from the first A operand; the rest come from the second (gemm2)
   int num_tiles;
   upnerf_epilogue ep;
   // lsu_store: finished 128 x 64 output boxes are copied out by the group's own threads (coalesced
@@ -80,9 +81,9 @@ __device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf
 // loop the plain N = K = 256 layer went from 0.159 to 0.181 ms.
 template <bool kRB, bool kHD>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-               const __grid_constant__ GemmArgs args) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ GemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -108,6 +109,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
+    if (args.kb1 < args.K / kBK) prefetch_tmap(&tmA2);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     if (has_aux) prefetch_tmap(&tmAux);
@@ -148,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], tx);
-          tma_load_2d(sA + stage * kABytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
+          if (kb < args.kb1) tma_load_2d(sA + stage * kABytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
+          else tma_load_2d(sA + stage * kABytes, &tmA2, &bar_full[stage], (kb - args.kb1) * kBK, tile * kBM);
           tma_load_2d(sB + stage * kBBytesMax, &tmB, &bar_full[stage], kb * kBK, 0);
           if (++stage == kStages) {
             stage = 0;
@@ -455,9 +458,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }  // namespace
 }  // namespace upnerf
 
+namespace upnerf {
+static int gemm_launch(const void* A, int64_t lda, int K1, const void* A2, int64_t lda2, const void* B, int64_t ldb,
+                       void* C, int64_t ldc, int64_t M, int N, int K, const upnerf_epilogue* ep, void* stream);
+}  // namespace upnerf
+
 extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                                 int64_t ldc, int64_t M, int N, int K, const upnerf_epilogue* ep,
                                 void* stream) {
+  return upnerf::gemm_launch(A, lda, K, nullptr, 0, B, ldb, C, ldc, M, N, K, ep, stream);
+}
+
+extern "C" int upnerf_gemm2_bf16(const void* A1, int64_t lda1, int K1, const void* A2, int64_t lda2, int K2,
+                                 const void* B, int64_t ldb, void* C, int64_t ldc, int64_t M, int N,
+                                 const upnerf_epilogue* ep, void* stream) {
+  using namespace upnerf;
+  UPNERF_REQUIRE(A2 && K1 >= 64 && K1 % 64 == 0 && K2 >= 64 && K2 % 64 == 0, UPNERF_ERR_BAD_SHAPE,
+                 "gemm2_bf16: K1=%d K2=%d must be positive multiples of 64", K1, K2);
+  return gemm_launch(A1, lda1, K1, A2, lda2, B, ldb, C, ldc, M, N, K1 + K2, ep, stream);
+}
+
+static int upnerf::gemm_launch(const void* A, int64_t lda, int K1, const void* A2, int64_t lda2, const void* B,
+                               int64_t ldb, void* C, int64_t ldc, int64_t M, int N, int K, const upnerf_epilogue* ep,
+                               void* stream) {
   using namespace upnerf;
   UPNERF_REQUIRE(M > 0, UPNERF_ERR_BAD_SHAPE, "gemm_bf16: M=%lld", (long long)M);
   UPNERF_REQUIRE(N >= 64 && N <= kMaxN && N % 64 == 0, UPNERF_ERR_BAD_SHAPE,
@@ -491,8 +514,11 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
     args.ldc = ldc;
     if ((reinterpret_cast<uintptr_t>(C) & 15) != 0 || (ldc & 7) != 0) args.lsu_store = 0;
   }
-  CUtensorMap tmA, tmB, tmC, tmAux;
-  UPNERF_TRY(make_tmap_bf16_2d(&tmA, A, M, K, lda, kBM, kBK));
+  args.kb1 = K1 / kBK;
+  CUtensorMap tmA, tmA2, tmB, tmC, tmAux;
+  UPNERF_TRY(make_tmap_bf16_2d(&tmA, A, M, K1, lda, kBM, kBK));
+  if (A2) UPNERF_TRY(make_tmap_bf16_2d(&tmA2, A2, M, K - K1, lda2, kBM, kBK));
+  else tmA2 = tmA;
   UPNERF_TRY(make_tmap_bf16_2d(&tmB, B, N, K, ldb, N, kBK));
   UPNERF_TRY(make_tmap_bf16_2d(&tmC, C, M, N, ldc, kBM, 64));
   if (args.ep.aux_mode != 0) {
@@ -500,7 +526,8 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   } else {
     tmAux = tmC;
   }
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmArgs);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                            const CUtensorMap, const GemmArgs);
   static const KernelFn kernels[4] = {gemm_tc_kernel<false, false>, gemm_tc_kernel<true, false>,
                                       gemm_tc_kernel<false, true>, gemm_tc_kernel<true, true>};
   static bool attr_set = false;
@@ -513,7 +540,7 @@ extern "C" int upnerf_gemm_bf16(const void* A, int64_t lda, const void* B, int64
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   LaunchScope scope(kCatGemmTc, as_stream(stream), 2.0 * M * N * K,
                     2.0 * M * (K + N * (args.ep.aux_mode ? 2 : 1)) + 2.0 * N * K);
-  fn<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmA, tmB, tmC, tmAux, args);
+  fn<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tmA, tmA2, tmB, tmC, tmAux, args);
   UPNERF_CHECK_LAUNCH("gemm_tc_kernel");
   return UPNERF_OK;
 }

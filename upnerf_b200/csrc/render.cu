@@ -203,8 +203,9 @@ void carve_pass(Bump& b, int64_t R, int S, size_t es, const NetLayout& L, bool k
     }
     k.WkT[0] = k.WkT[4] = nullptr;
   }
-  k.W1T = b.take_bytes(PEW * W * es);
-  k.W5peT = b.take_bytes(PEW * W * es);
+  // [W5pe^T | W1^T] side by side along K ([64, 512], row stride 2W): dPE is ONE GEMM over [dY5 | dY1]
+  k.W5peT = b.take_bytes(PEW * 2 * W * es);
+  k.W1T = k.W5peT ? static_cast<uint8_t*>(k.W5peT) + W * es : nullptr;
   k.Wcq = b.take_bytes(2 * H * W * es);
   k.Wc1 = k.Wcq;
   k.Wq = k.Wcq ? static_cast<uint8_t*>(k.Wcq) + static_cast<uint64_t>(H) * W * es : nullptr;
@@ -455,7 +456,7 @@ int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, cons
   const int ix = L.in_xyz;
   // layer 1: [256, in_xyz] -> [256, 64] (zero padded) and its transpose [64, 256]
   add(prm + L.Wl[0], ix, k.W1, WCAT, W, ix, 0);
-  add(prm + L.Wl[0], ix, k.W1T, W, W, ix, 1);
+  add(prm + L.Wl[0], ix, k.W1T, 2 * W, W, ix, 1);
   for (int i = 1; i < 8; ++i) {
     if (i == 4) continue;
     add(prm + L.Wl[i], W, k.Wk[i], WCAT, W, W, 0);
@@ -465,7 +466,7 @@ int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, cons
   add(prm + L.Wl[4] + ix, W + ix, k.W5, WCAT, W, W, 0);
   add(prm + L.Wl[4], W + ix, col(k.W5, W, c.es), WCAT, W, ix, 0);
   add(prm + L.Wl[4] + ix, W + ix, k.W5T, WCATT, W, W, 1);
-  add(prm + L.Wl[4], W + ix, k.W5peT, W, W, ix, 1);
+  add(prm + L.Wl[4], W + ix, k.W5peT, 2 * W, W, ix, 1);
   add(prm + L.Wf, W, k.WF, WCAT, W, W, 0);
   add(prm + L.Wf, W, k.WFT, WCATT, W, W, 1);
   UPNERF_TRY(run_pack(pl, c.dtype, c.st));
@@ -887,18 +888,22 @@ int pass_bwd(const Ctx& c, const upnerf_render_args& a, const NetLayout& L, cons
         e.aux = p.X4; e.ldaux = X4W; e.aux_mode = 2;
         UPNERF_TRY(linear(c, dcur, W, k.W5T, WCATT, dnext, W, M, W, W, e));
       }
-      if (a.d_rays) {
+      if (a.d_rays && !fused) {
         e = ep_none();
-        UPNERF_TRY(linear(c, dcur, W, k.W5peT, W, s.dPE, PEW, M, PEW, W, e));
+        UPNERF_TRY(linear(c, dcur, W, k.W5peT, 2 * W, s.dPE, PEW, M, PEW, W, e));
         dpe_live = true;
       }
     } else if (i == 0) {
       const Seg sg{0, L.in_xyz, 0};
       if (wg) UPNERF_TRY(wgrad(c, dcur, W, PE, X4W, g + L.Wl[0], L.in_xyz, g + L.bl[0], M, W, PEW, &sg, 1));
-      if (a.d_rays) {
+      if (a.d_rays && fused) {
+        // dPE = dY5 W5[:, pe] + dY1 W1 in one pass over [dY5 | dY1] (the two layers that read the encoding)
+        e = ep_none();
+        UPNERF_TRY(upnerf_gemm2_bf16(s.dY[3], W, W, dcur, W, W, k.W5peT, 2 * W, s.dPE, PEW, M, PEW, &e, c.st));
+      } else if (a.d_rays) {
         e = ep_none();
         if (dpe_live) { e.aux = s.dPE; e.ldaux = PEW; e.aux_mode = 1; }
-        UPNERF_TRY(linear(c, dcur, W, k.W1T, W, s.dPE, PEW, M, PEW, W, e));
+        UPNERF_TRY(linear(c, dcur, W, k.W1T, 2 * W, s.dPE, PEW, M, PEW, W, e));
       }
     } else {
       const Seg sg{0, W, 0};
