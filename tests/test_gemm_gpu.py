@@ -203,17 +203,16 @@ def _trunk_reference(pe, ws, bs, sw, sb):
     return outs, sig
 
 
-@pytest.mark.parametrize("variant", ["dual", "multicast", "2sm", "multicast-tma-store", "multicast-epilogue-copy"])
+@pytest.mark.parametrize("variant", ["multicast", "single-cta", "multicast-tma-store", "multicast-epilogue-copy"])
 @pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1, 128 * 148 * 5 + 77])
 def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
-    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around),
-    for the three forward kernels: dual-tile cta_group::2 (default), single-tile CTA pairs sharing the
-    weight stream by multicast (UPNERF_TRUNK_DUAL=0) and single-tile cta_group::2 (+UPNERF_TRUNK_2SM=1)."""
+    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around), for
+    CTA pairs sharing the weight stream by multicast (default), single CTAs (UPNERF_TRUNK_CLUSTER=1) and the
+    three activation store paths."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_DUAL", "1" if variant == "dual" else "0")
-    monkeypatch.setenv("UPNERF_TRUNK_2SM", "1" if variant == "2sm" else "0")
+    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant == "single-cta" else "2")
     # activation store path of the default kernel: 2 = copy-out warps (default), 0 = TMA stores, 1 = epilogue copy
     monkeypatch.setenv("UPNERF_TRUNK_LSU_STORE", {"multicast-tma-store": "0", "multicast-epilogue-copy": "1"}.get(variant, "2"))
 

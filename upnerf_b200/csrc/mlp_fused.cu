@@ -61,7 +61,7 @@ constexpr int kOffBias = kOffW + kWStages * kWBytes;
 constexpr int kOffHeadW = kOffBias + kNL * 256 * 4;
 constexpr int kOffHead = kOffHeadW + 256 * 4;
 constexpr int kOffBar = kOffHead + 4 * kTileM * 4;
-constexpr int kMaxWStages = 6;               // pair mode: six 16 KB half-chunk stages in the same 96 KB
+constexpr int kMaxWStages = kWStages;
 constexpr int kNumBars = 2 * kMaxWStages + 4 + kChunks + 2 + 8;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;
@@ -110,13 +110,10 @@ __device__ __forceinline__ float softplus_ref(float x) {
 // it into both CTAs, which halves the L2 -> shared-memory traffic (the first bound this kernel
 // hits: 1.06 MB of weights per 128-sample tile).
 //
-// k2Sm (kCluster = 2 only): the pair runs ONE tcgen05.mma.cta_group::2 per K step -- M = 256 (128 rows
-// from each CTA's activation tile), N = 256 with each CTA holding only ITS 128 output features of the
-// weight chunk (16 KB instead of 32 KB: the per-SM operand reads of every MMA drop from 12 KB to 8 KB
-// and the weight fill of shared memory halves).  The leader CTA's MMA thread issues for both; its
-// barriers collect both CTAs' TMA bytes (cp.async.bulk.tensor.cta_group::2) and both CTAs' epilogue
-// arrivals (remote mbarrier.arrive), and every commit is multicast to both CTAs.
-template <int kCluster, bool k2Sm = false>
+// (Two tcgen05.mma.cta_group::2 variants of this kernel -- a pair MMA over both CTAs' tiles, and a dual-tile
+// version with two pair tiles in flight -- were built, parity-tested and measured in rounds 1 and 2: 1.42 /
+// 1.27 ms against 1.03-1.09 ms for this one at M = 786k.  They were removed; DESIGN.md section 5 has the numbers.)
+template <int kCluster>
 __global__ void __launch_bounds__(kThreadsF, 1)
 mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -129,9 +126,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
   float* sHeadW = reinterpret_cast<float*>(smem + kOffHeadW);
   float* sHead = reinterpret_cast<float*>(smem + kOffHead);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  static_assert(!k2Sm || kCluster == 2, "the pair MMA needs a cluster of two");
-  constexpr int kStages = k2Sm ? kMaxWStages : kWStages;
-  constexpr int kStageBytes = k2Sm ? kWBytes / 2 : kWBytes;
+  constexpr int kStages = kWStages;
+  constexpr int kStageBytes = kWBytes;
   uint64_t* bar_wfull = bars;
   uint64_t* bar_wempty = bars + kMaxWStages;
   uint64_t* bar_pefull = bars + 2 * kMaxWStages;
@@ -159,25 +155,22 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     for (int i = 0; i < kNL; ++i) prefetch_tmap(&maps.out[i]);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bar_wfull[i], 1);
-      mbar_init(&bar_wempty[i], k2Sm ? 1 : kCluster);   // pair mode: one multicast commit from the leader
+      mbar_init(&bar_wempty[i], kCluster);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_pefull[i], 1);
       mbar_init(&bar_peempty[i], 1);
       mbar_init(&bar_tfull[i], 1);
     }
-    // one per output box: the 8 warps of a set (pair mode: of both CTAs, on the leader's barrier)
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], k2Sm ? 16 : 8);
+    // one per output box: the 8 warps of a set
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bar_st[i], 8);
       mbar_init(&bar_stfree[i], kCopyWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    if (k2Sm) tmem_alloc_2sm<512>(tmem_holder);
-    else tmem_alloc<512>(tmem_holder);
-  }
+  if (warp == 1) tmem_alloc<512>(tmem_holder);
   if (warp >= 2 && warp < 18) {
     const int t = threadIdx.x - 64;
     for (int i = t; i < kNL * 256; i += kEpiThreads) {
@@ -199,12 +192,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       uint32_t wph = 0;
       auto load_w = [&](int kcol) {
         mbar_wait(&bar_wempty[ws], wph ^ 1);
-        if (k2Sm) {
-          // my 128 output features of the chunk, counted on the LEADER's barrier (which expects both halves)
-          if (cta_rank == 0) mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
-          tma_load_2d_2sm(sW + ws * kStageBytes, &maps.w, mapa_u32(smem_u32(&bar_wfull[ws]), 0), kcol,
-                          cta_rank * 128);
-        } else if (kCluster == 1) {
+        if (kCluster == 1) {
           mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
           tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
         } else {
@@ -221,14 +209,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       auto load_pe = [&](int t, int tile) {
         const int slot = t & 1;
         mbar_wait(&bar_peempty[slot], ((t >> 1) & 1) ^ 1);
-        if (k2Sm) {
-          if (cta_rank == 0) mbar_arrive_expect_tx(&bar_pefull[slot], 2 * kBoxBytes);
-          tma_load_2d_2sm(sPE + slot * kBoxBytes, &maps.pe, mapa_u32(smem_u32(&bar_pefull[slot]), 0), 0,
-                          tile * kTileM);
-        } else {
-          mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
-          tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
-        }
+        mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
+        tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
       };
       int t = 0;
       if (unit0 < num_units) load_pe(0, unit0 * kCluster + cta_rank);
@@ -252,8 +234,8 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     // diverged lane needed ~200 cycles of R2UR / ELECT / address math per MMA (ncu source view: 63 % of
     // the issuing thread's samples in issue code, tensor pipe 35 % active) -- the issue thread, not
     // the epilogue, paced the kernel.
-    if (!k2Sm || cta_rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(k2Sm ? 2 * kTileM : kTileM, 256, 0, 0);
+    {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
       int ws = 0;
       uint32_t wph = 0;
       uint32_t act_ph = 0;
@@ -261,17 +243,13 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
       int t = 0;
       auto free_stage = [&](uint64_t* bar) {
         if (elect_one()) {
-          if (k2Sm) mma_commit_2sm_mc(bar, kMask);
-          else if (kCluster == 1) mma_commit(bar);
+          if (kCluster == 1) mma_commit(bar);
           else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
         }
         __syncwarp();
       };
-      auto commit_local = [&](uint64_t* bar) {   // pair mode: the peer's producer / epilogue wait on it too
-        if (elect_one()) {
-          if (k2Sm) mma_commit_2sm_mc(bar, kMask);
-          else mma_commit(bar);
-        }
+      auto commit_local = [&](uint64_t* bar) {
+        if (elect_one()) mma_commit(bar);
         __syncwarp();
       };
       auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t& accum) {
@@ -280,8 +258,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t db = umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128);
-            if (k2Sm) mma_bf16_ss_2sm(d, da, db, idesc, (k > 0) ? 1u : accum);
-            else mma_bf16_ss(d, da, db, idesc, (k > 0) ? 1u : accum);
+            mma_bf16_ss(d, da, db, idesc, (k > 0) ? 1u : accum);
           }
         }
         __syncwarp();
@@ -312,8 +289,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
               mbar_wait(&bar_wfull[ws], wph);
-              if (k2Sm) mbar_wait_cluster(&bar_act[b], act_ph);
-              else mbar_wait(&bar_act[b], act_ph);
+              mbar_wait(&bar_act[b], act_ph);
               tc_fence_after_sync();
               const uint32_t a_addr = smem_u32(sAct + b * kBoxBytes);
               const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
@@ -397,8 +373,6 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
     const uint32_t sbias = smem_u32(sBias);
     const uint32_t sheadw = smem_u32(sHeadW);
     const uint32_t swz = row & 7;
-    // pair mode: "box written" goes to the leader CTA's barrier (its MMA thread issues for both CTAs)
-    const uint32_t act_bar0 = k2Sm ? mapa_u32(smem_u32(&bar_act[0]), 0) : 0;
     // copy-out mapping (lsu_store): lane -> row cp_row0 + 4 i (i = 0..3) of the box, 16-byte chunk lane % 8.
     // Row r keeps chunk c at position c ^ (r & 7); (r & 7) = lane / 8 for even i and lane / 8 + 4 for odd i.
     const int cp_row0 = (ew & 7) * 16 + (lane >> 3);
@@ -482,10 +456,7 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             if (feeds) {
               tc_fence_before_sync();
               __syncwarp();
-              if (lane0) {                             // one arrival per warp
-                if (k2Sm) mbar_arrive_cluster(act_bar0 + box * 8);
-                else mbar_arrive(&bar_act[box]);
-              }
+              if (lane0) mbar_arrive(&bar_act[box]);   // one arrival per warp
             }
             // (after the hand-off: the proxy fence above is a full CTA membar and would otherwise wait
             // for this global store's round trip before the MMA warp hears about the box)
@@ -537,424 +508,10 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
   if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still signal it
   if (warp == 1) {
     tc_fence_after_sync();
-    if (k2Sm) tmem_dealloc_2sm<512>(tmem_base);
-    else tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
-// =====================================================================================
-// Dual-tile pair kernel: two 256-row pair tiles in flight per CTA pair.
-//
-// The single-tile kernel above is bound by the serial chain of a tile: the MMAs of layer l+1 wait for
-// the epilogue of layer l and vice versa (ncu: tensor pipe 35 %, issue slots 31 %, no unit
-// saturated).  Here every CTA pair works on TWO pair tiles (slots A, B: 2 x 128 rows per CTA, one
-// 256-column accumulator each -- all 512 TMEM columns) and strictly alternates
-//     MMA      : A(l)   B(l)   A(l+1) B(l+1) ...
-//     epilogue :        A(l)   B(l)   A(l+1) ...
-// so the epilogue of one slot runs under the MMAs of the other.  Shared memory only fits this with
-// the cta_group::2 operand split (each CTA stages its 128 output features of a weight chunk: 16 KB
-// stages): 2 x 64 KB activation tiles + 2 x 16 KB PE tiles + 3 x 16 KB weight stages + biases.
-// Hand-offs are per layer and slot (the first MMA of a layer overwrites the whole accumulator, so
-// it waits for "accumulator drained" = bar_tempty, and for the four "box written" barriers).
-namespace dual {
-
-constexpr int kStages = 3;
-constexpr int kStageBytes = kWBytes / 2;
-constexpr int kOffAct2 = 0;                               // [2 slots][4 boxes]
-constexpr int kOffPE2 = kOffAct2 + 2 * kActBytes;         // [2 slots]
-constexpr int kOffW2 = kOffPE2 + 2 * kBoxBytes;
-constexpr int kOffBias2 = kOffW2 + kStages * kStageBytes;
-constexpr int kOffHeadW2 = kOffBias2 + kNL * 256 * 4;
-constexpr int kOffHead2 = kOffHeadW2 + 256 * 4;
-constexpr int kOffBar2 = kOffHead2 + 4 * kTileM * 4;
-// wfull[3] wempty[3] pefull[2] peempty[2] act[2][4] tfull[2] tempty[2] st[2][4] stfree[2][4]
-constexpr int kNumBars2 = 2 * kStages + 4 + 8 + 4 + 16;
-constexpr int kOffTmem2 = kOffBar2 + kNumBars2 * 8;
-constexpr int kSmemBytes2 = kOffTmem2 + 16 + 1024;
-static_assert(kSmemBytes2 <= 232448, "shared memory budget exceeded");
-
-__global__ void __launch_bounds__(kThreadsF, 1)
-mlp_trunk_fwd_dual_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sAct = smem + kOffAct2;
-  uint8_t* sPE = smem + kOffPE2;
-  uint8_t* sW = smem + kOffW2;
-  float* sBias = reinterpret_cast<float*>(smem + kOffBias2);
-  float* sHeadW = reinterpret_cast<float*>(smem + kOffHeadW2);
-  float* sHead = reinterpret_cast<float*>(smem + kOffHead2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar2);
-  uint64_t* bar_wfull = bars;
-  uint64_t* bar_wempty = bars + kStages;
-  uint64_t* bar_pefull = bars + 2 * kStages;
-  uint64_t* bar_peempty = bar_pefull + 2;
-  uint64_t* bar_act = bar_peempty + 2;      // [slot * 4 + box], on the leader: 8 warps of a set x 2 CTAs
-  uint64_t* bar_tfull = bar_act + 8;        // [slot] accumulator complete (commit, multicast to both CTAs)
-  uint64_t* bar_tempty = bar_tfull + 2;     // [slot] accumulator drained, on the leader: 16 warps x 2 CTAs
-  uint64_t* bar_st = bar_tempty + 2;        // [slot * 4 + box] lsu_store == 2: box written (8 warps of its set) -> copy-out warps
-  uint64_t* bar_stfree = bar_st + 8;        // [slot * 4 + box] box copied out (kCopyWarps arrivals) -> may be overwritten
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int cta_rank = static_cast<int>(cluster_ctarank());
-  // a unit = two pair tiles = four 128-row tiles; pair tile p covers tiles 2p (CTA 0) and 2p+1 (CTA 1)
-  const int unit0 = blockIdx.x / 2;
-  const int unit_step = gridDim.x / 2;
-  const int num_units = (args.num_tiles + 3) / 4;
-  constexpr uint16_t kMask = 3;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&maps.w);
-    prefetch_tmap(&maps.pe);
-    for (int i = 0; i < kNL; ++i) prefetch_tmap(&maps.out[i]);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bar_wfull[i], 1);
-      mbar_init(&bar_wempty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_pefull[i], 1);
-      mbar_init(&bar_peempty[i], 1);
-      mbar_init(&bar_tfull[i], 1);
-      // accumulator drained: my 16 epilogue warps (+ on the leader one relayed arrival for the peer's 16)
-      mbar_init(&bar_tempty[i], 16 + (cta_rank == 0 ? 1 : 0));
-    }
-    // box written: the 8 warps of the owning set (+ on the leader one relayed arrival for the peer's box)
-    for (int i = 0; i < 8; ++i) mbar_init(&bar_act[i], 8 + (cta_rank == 0 ? 1 : 0));
-    for (int i = 0; i < 8; ++i) {
-      mbar_init(&bar_st[i], 8);
-      mbar_init(&bar_stfree[i], kCopyWarps);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc_2sm<512>(tmem_holder);
-  if (warp >= 2 && warp < 18) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < kNL * 256; i += kEpiThreads) {
-      const float* b = args.bias[i >> 8];
-      sBias[i] = b ? b[i & 255] : 0.f;
-    }
-    for (int i = t; i < 256; i += kEpiThreads) sHeadW[i] = args.head_w ? args.head_w[i] : 0.f;
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_holder;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs: own halves)
-    if (lane == 0) {
-      int ws = 0;
-      uint32_t wph = 0;
-      auto load_w = [&](int kcol) {
-        mbar_wait(&bar_wempty[ws], wph ^ 1);
-        if (cta_rank == 0) mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);   // both halves
-        tma_load_2d_2sm(sW + ws * kStageBytes, &maps.w, mapa_u32(smem_u32(&bar_wfull[ws]), 0), kcol,
-                        cta_rank * 128);
-        if (++ws == kStages) {
-          ws = 0;
-          wph ^= 1;
-        }
-      };
-      auto load_pe = [&](int t, int slot, int unit) {
-        mbar_wait(&bar_peempty[slot], (t & 1) ^ 1);
-        if (cta_rank == 0) mbar_arrive_expect_tx(&bar_pefull[slot], 2 * kBoxBytes);
-        const int tile = (unit * 2 + slot) * 2 + cta_rank;
-        tma_load_2d_2sm(sPE + slot * kBoxBytes, &maps.pe, mapa_u32(smem_u32(&bar_pefull[slot]), 0), 0,
-                        tile * kTileM);
-      };
-      int t = 0;
-      if (unit0 < num_units) {
-        load_pe(0, 0, unit0);
-        load_pe(0, 1, unit0);
-      }
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        for (int l = 0; l < kNL; ++l) {
-          const LayerDesc& L = args.layer[l];
-          if (l == 6 && unit + unit_step < num_units) {   // both slots' PE tiles are free since layer 5
-            load_pe(t + 1, 0, unit + unit_step);
-            load_pe(t + 1, 1, unit + unit_step);
-          }
-          for (int slot = 0; slot < 2; ++slot) {
-            if (L.w_pe >= 0) load_w(L.w_pe);
-            if (L.w_act >= 0)
-              for (int b = 0; b < 4; ++b) load_w(L.w_act + b * 64);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    // Warp-uniform loop, one elected lane issues (see the single-tile kernel: a single diverged lane spends
-    // ~200 cycles of address / descriptor arithmetic per MMA, which alone paced this kernel before).
-    if (cta_rank != 0) {
-      // Relay (the peer CTA's otherwise idle MMA warp): the epilogue warps of BOTH CTAs only ever arrive on
-      // barriers of their own CTA -- a cluster-scope release arrive from every epilogue warp (three per warp,
-      // layer and slot) made the epilogue itself ~2x slower.  This warp waits for the peer's local barriers in
-      // the order the leader's issuer consumes them and forwards ONE remote arrival each.
-      const uint32_t act_bar0 = mapa_u32(smem_u32(&bar_act[0]), 0);
-      const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
-      uint32_t act_ph[2] = {0, 0};
-      uint32_t gs = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
-        for (int l = 0; l < kNL; ++l, ++gs) {
-          const LayerDesc& L = args.layer[l];
-          for (int slot = 0; slot < 2; ++slot) {
-            if (gs > 0) {       // (the very first use of an accumulator has no drain to wait for)
-              mbar_wait(&bar_tempty[slot], (gs & 1) ^ 1);
-              if (lane == 0) mbar_arrive_cluster(tempty0 + slot * 8);
-              __syncwarp();
-            }
-            if (L.w_act >= 0) {
-              for (int b = 0; b < 4; ++b) {
-                mbar_wait(&bar_act[slot * 4 + b], act_ph[slot]);
-                if (lane == 0) mbar_arrive_cluster(act_bar0 + (slot * 4 + b) * 8);
-                __syncwarp();
-              }
-              act_ph[slot] ^= 1;
-            }
-          }
-        }
-      }
-    } else {
-      const uint32_t idesc = umma_idesc_bf16(2 * kTileM, 256, 0, 0);
-      int ws = 0;
-      uint32_t wph = 0;
-      uint32_t act_ph[2] = {0, 0};
-      uint32_t gs = 0;   // layers issued so far per slot (same for both)
-      int t = 0;
-      auto commit = [&](uint64_t* bar) {
-        if (elect_one()) mma_commit_2sm_mc(bar, kMask);
-        __syncwarp();
-      };
-      auto next_stage = [&]() {
-        commit(&bar_wempty[ws]);
-        if (++ws == kStages) {
-          ws = 0;
-          wph ^= 1;
-        }
-      };
-      auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t& accum) {
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_bf16_ss_2sm(d, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                            umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, (k > 0) ? 1u : accum);
-        }
-        __syncwarp();
-        accum = 1;
-      };
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        for (int l = 0; l < kNL; ++l, ++gs) {
-          const LayerDesc& L = args.layer[l];
-          for (int slot = 0; slot < 2; ++slot) {
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            // the epilogue (both CTAs) has read the previous layer of this slot out of the accumulator
-            mbar_wait_cluster(&bar_tempty[slot], (gs & 1) ^ 1);
-            tc_fence_after_sync();
-            uint32_t accum = 0;
-            if (L.w_pe >= 0) {
-              mbar_wait(&bar_pefull[slot], t & 1);
-              mbar_wait(&bar_wfull[ws], wph);
-              tc_fence_after_sync();
-              mma4(d_tmem, smem_u32(sPE + slot * kBoxBytes), smem_u32(sW + ws * kStageBytes), accum);
-              next_stage();
-              if (L.pe_last) commit(&bar_peempty[slot]);
-            }
-            if (L.w_act >= 0) {
-#pragma unroll 1
-              for (int b = 0; b < 4; ++b) {
-                mbar_wait(&bar_wfull[ws], wph);
-                mbar_wait_cluster(&bar_act[slot * 4 + b], act_ph[slot]);
-                tc_fence_after_sync();
-                mma4(d_tmem, smem_u32(sAct + slot * kActBytes + b * kBoxBytes), smem_u32(sW + ws * kStageBytes), accum);
-                next_stage();
-              }
-              act_ph[slot] ^= 1;
-            }
-            commit(&bar_tfull[slot]);
-          }
-        }
-      }
-    }
-  } else if (warp >= 18) {
-    // ------------------------------------------------------------ copy-out warps (lsu_store == 2), see the single-tile kernel
-    if (args.lsu_store == 2) {
-      const int cw = warp - 18;
-      constexpr int kRowsPer = kTileM / kCopyWarps;           // 64
-      const int r0 = cw * kRowsPer + (lane >> 3);
-      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
-      const uint32_t so_even = r0 * 128 + x0, so_odd = r0 * 128 + (x0 ^ 64u);
-      uint32_t ph = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
-        for (int l = 0; l < kNL; ++l) {
-          if (!args.layer[l].store) continue;
-          const int64_t ldo = args.ld_out[l];
-          for (int slot = 0; slot < 2; ++slot) {
-            const int tile = (unit * 2 + slot) * 2 + cta_rank;
-            const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;
-            __nv_bfloat16* o0 = args.out[l] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
-            for (int b = 0; b < 4; ++b) {
-              mbar_wait(&bar_st[slot * 4 + b], ph);
-              const uint32_t sbox = smem_u32(sAct) + slot * kActBytes + b * kBoxBytes;
-              __nv_bfloat16* ob = o0 + b * 64;
-#pragma unroll
-              for (int h = 0; h < kRowsPer / 32; ++h) {
-                float4 vv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  vv[i] = lds128(sbox + ((i & 1) ? so_odd : so_even) + (h * 8 + i) * 512);
-                if (h == kRowsPer / 32 - 1) {
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(&bar_stfree[slot * 4 + b]);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (r0 + (h * 8 + i) * 4 < rows_left)
-                    __stcs(reinterpret_cast<float4*>(ob + static_cast<int64_t>((h * 8 + i) * 4) * ldo), vv[i]);
-              }
-            }
-          }
-          ph ^= 1;
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue warps (as in the single-tile kernel)
-    const int ew = warp - 2;
-    const int grp = ew >> 2;
-    const int half = grp & 1;
-    const int set = grp >> 1;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const bool lane0 = lane_id() == 0;
-    const bool leader = ((ew & 7) == 0) && lane0;
-    const uint32_t set_bar = 2 + set;
-    const uint32_t sbias = smem_u32(sBias);
-    const uint32_t sheadw = smem_u32(sHeadW);
-    const uint32_t swz = row & 7;
-    uint32_t gs = 0;
-    uint32_t nst = 0;   // lsu_store == 2: stored layers so far (= releases seen per (slot, box))
-    for (int unit = unit0; unit < num_units; unit += unit_step) {
-      for (int l = 0; l < kNL; ++l, ++gs) {
-        const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
-        const int store = args.layer[l].store;
-        for (int slot = 0; slot < 2; ++slot) {
-          const int tile = (unit * 2 + slot) * 2 + cta_rank;
-          const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
-          uint8_t* sActS = sAct + slot * kActBytes;
-          const uint32_t sact_row = smem_u32(sActS) + row * 128;
-          mbar_wait(&bar_tfull[slot], gs & 1);
-          tc_fence_after_sync();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * 256;
-          const bool want_mask = relu && args.relu_mask != nullptr;
-          uint32_t mbits = 0;
-          float hacc = 0.f;
-          uint32_t r[2][16];
-          tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int box = set + (q & 2);
-            const int col0 = box * 64 + half * 32 + (q & 1) * 16;
-            // copy-out warps: the previous contents of this box must have been read out before my first write
-            if (args.lsu_store == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[slot * 4 + box], (nst - 1) & 1);
-            tmem_ld_wait_dep(r[q & 1]);
-            if (q < 3) {
-              const int nbox = set + ((q + 1) & 2);
-              tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
-            }
-            const uint32_t* rr = r[q & 1];
-            float v[16];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 b4 = lds128(sbias + (l * 256 + col0 + k * 4) * 4);
-              v[k * 4 + 0] = __uint_as_float(rr[k * 4 + 0]) + b4.x;
-              v[k * 4 + 1] = __uint_as_float(rr[k * 4 + 1]) + b4.y;
-              v[k * 4 + 2] = __uint_as_float(rr[k * 4 + 2]) + b4.z;
-              v[k * 4 + 3] = __uint_as_float(rr[k * 4 + 3]) + b4.w;
-            }
-            if (q == 3) {
-              // my last TMEM read of this layer has landed in registers: the accumulator may be reused
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_tempty[slot]);
-            }
-            if (relu) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            if (head) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 w4 = lds128(sheadw + (col0 + k * 4) * 4);
-                hacc += v[k * 4] * w4.x + v[k * 4 + 1] * w4.y + v[k * 4 + 2] * w4.z + v[k * 4 + 3] * w4.w;
-              }
-            }
-            uint4 o[2];
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            const uint32_t box_row = sact_row + box * kBoxBytes;
-            const uint32_t s0 = half * 4 + (q & 1) * 2;
-            sts128(box_row + ((s0 ^ swz) << 4), o[0]);
-            sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
-            if (want_mask) {
-              // bit e = [column e > 0]: v >= +0 after the ReLU, so the sign of the negated bit pattern is the predicate
-              uint32_t m16 = 0;
-#pragma unroll
-              for (int e = 15; e >= 0; --e)
-                m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
-              mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
-            }
-            if (q & 1) {
-              fence_proxy_async_smem();
-              if (feeds) {
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane0) mbar_arrive(&bar_act[slot * 4 + box]);
-              }
-              if (want_mask)
-                args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
-              if (store && args.lsu_store == 2) {
-                __syncwarp();
-                if (lane0) mbar_arrive(&bar_st[slot * 4 + box]);   // the copy-out warps take it from here
-              } else if (store) {
-                if (leader) tma_store_wait_read<0>();
-                named_bar_sync(set_bar, kSetThreads);
-                if (leader) {
-                  tma_store_2d(&maps.out[l], sActS + box * kBoxBytes, box * 64, tile * kTileM);
-                  tma_store_commit();
-                }
-              }
-            }
-          }
-          if (head) {
-            sHead[grp * kTileM + row] = hacc;
-            named_bar_sync(4, kEpiThreads);
-            if (grp == 0 && grow < args.M)
-              args.head_out[grow] = softplus_ref(sHead[row] + sHead[kTileM + row] + sHead[2 * kTileM + row] +
-                                                 sHead[3 * kTileM + row] + args.head_b[0]);
-            named_bar_sync(4, kEpiThreads);   // sHead is rewritten by the other slot right after
-          }
-        }
-        if (store) ++nst;
-      }
-    }
-    if (leader) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc_2sm<512>(tmem_base);
-  }
-}
-
-}  // namespace dual
 
 // =====================================================================================
 // Backward data-gradient chain of the trunk -- upnerf_mlp_trunk_bwd_bf16.
@@ -1299,26 +856,6 @@ int trunk_cluster_size() {
   v = (e && e[0] == '1') ? 1 : 2;
   return v;
 }
-// UPNERF_TRUNK_2SM=1 selects the cta_group::2 forward (one pair MMA per K step, see the kernel
-// comment).  Measured on B200 at M = 786,432: 1.42 ms against 1.19 ms for the default (pairs that
-// only share the weight stream by multicast and issue their own cta_group::1 MMAs) -- the layer
-// chain is serial per tile (MMA of layer l+1 waits for the epilogue of layer l, box by box), and the
-// cross-SM hops the pair adds to that handoff (remote mbarrier arrive -> cluster-scope wait; the
-// accumulator-ready commit fanned out to both CTAs) cost more than the halved operand traffic saves.
-// Kept as a tested variant: it becomes the right shape once two tiles are interleaved per CTA.
-// Read on every call so a test can toggle it.
-// UPNERF_TRUNK_DUAL=1 selects the dual-tile pair kernel (two pair tiles in flight per CTA pair, see
-// namespace dual).  Measured on B200 at M = 786,432: 1.38 ms (1.64 ms with the ReLU masks) against
-// 1.19 / 1.25 ms for the default single-tile kernel, so it stays opt-in; tests cover all three.
-bool trunk_dual() {
-  const char* e = getenv("UPNERF_TRUNK_DUAL");
-  return e && e[0] == '1' && trunk_cluster_size() == 2;
-}
-bool trunk_two_sm() {
-  const char* e = getenv("UPNERF_TRUNK_2SM");
-  return e && e[0] == '1' && trunk_cluster_size() == 2;
-}
-
 }  // namespace
 }  // namespace upnerf
 
@@ -1378,10 +915,6 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
                                            kSmemBytes));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(dual::mlp_trunk_fwd_dual_kernel,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, dual::kSmemBytes2));
     attr_set = true;
   }
   const double flop = 2.0 * a->M * 256.0 * (64 + 7 * 256 + 320);
@@ -1393,24 +926,6 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   if (cluster == 1) {
     const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
     mlp_trunk_fwd_kernel<1><<<grid, kThreadsF, kSmemBytes, as_stream(stream)>>>(maps, args);
-  } else if (trunk_dual()) {
-    const int64_t units = ceil_div64(tiles, 4);
-    const int max_clusters = sm_count() / 2;
-    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreadsF);
-    cfg.dynamicSmemBytes = dual::kSmemBytes2;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dual::mlp_trunk_fwd_dual_kernel, maps, args));
   } else {
     const int64_t units = ceil_div64(tiles, 2);
     const int max_clusters = sm_count() / 2;
@@ -1428,18 +943,17 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (trunk_two_sm()) UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2, true>, maps, args));
-    else UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
+    UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
   }
   UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_kernel");
   return UPNERF_OK;
 }
 
 extern "C" int64_t upnerf_trunk_mask_words(int64_t M) {
-  // tiles are processed in units of CTA pairs (x two slots): CTAs whose tile index is past the end
-  // write (all-zero) masks for phantom tiles, so the buffer covers a whole number of units
+  // tiles are processed in units of CTA pairs: a CTA whose tile index is past the end writes (all-zero) masks
+  // for a phantom tile, so the buffer covers a whole number of units (rounded to four tiles: the ABI's historic size)
   const int64_t tiles = upnerf::ceil_div64(M, upnerf::kTileM);
-  return ((tiles + 3) / 4) * 4 * 8 * 8 * upnerf::kTileM;    // dual-tile pairs: four tiles per unit
+  return ((tiles + 3) / 4) * 4 * 8 * 8 * upnerf::kTileM;
 }
 
 extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* stream) {
