@@ -203,17 +203,20 @@ def _trunk_reference(pe, ws, bs, sw, sb):
     return outs, sig
 
 
-@pytest.mark.parametrize("variant", ["multicast", "single-cta", "multicast-tma-store", "multicast-epilogue-copy"])
+@pytest.mark.parametrize("variant", ["multicast", "single-cta", "multicast-tma-store", "multicast-epilogue-copy",
+                                     "multicast-single-tile", "single-cta-single-tile"])
 @pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1, 128 * 148 * 5 + 77])
 def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
-    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around), for
-    CTA pairs sharing the weight stream by multicast (default), single CTAs (UPNERF_TRUNK_CLUSTER=1) and the
-    three activation store paths."""
+    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around), for the
+    default kernel (two tiles in flight per CTA, CTA pairs sharing the weight stream by multicast), the same with
+    single CTAs (UPNERF_TRUNK_CLUSTER=1), and the one-tile-per-CTA kernel with its three activation store paths."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant == "single-cta" else "2")
-    # activation store path of the default kernel: 2 = copy-out warps (default), 0 = TMA stores, 1 = epilogue copy
+    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant.startswith("single-cta") else "2")
+    # default: two tiles in flight per CTA; "-single-tile" (and every store path but the copy-out warps): one tile
+    monkeypatch.setenv("UPNERF_TRUNK_PP", "0" if variant.endswith("single-tile") else "1")
+    # activation store path: 2 = copy-out warps (default), 0 = TMA stores, 1 = epilogue copy (both single-tile only)
     monkeypatch.setenv("UPNERF_TRUNK_LSU_STORE", {"multicast-tma-store": "0", "multicast-epilogue-copy": "1"}.get(variant, "2"))
 
     g = torch.Generator(device="cpu").manual_seed(M)
@@ -244,8 +247,8 @@ def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     assert torch.allclose(sig, ref_sig, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("store", ["0", "1", "2"])
-@pytest.mark.parametrize("M", [128 * 2 + 77, 128 * 148 * 2 + 128 * 3 + 9])
+@pytest.mark.parametrize("store", ["0", "1", "2", "2-single-tile", "2-single-cta"])
+@pytest.mark.parametrize("M", [128 * 2 + 77, 128 * 148 * 2 + 128 * 3 + 9, 128 * 148 * 5 + 77])
 def test_mlp_trunk_bwd_fused(cuda_dev, M, store, monkeypatch):
     """Fused backward chain: dY8 = (dHF W_F + dssig (x) w_s) * [H8>0], dYl = (dY(l+1) W(l+1)) * [Hl>0],
     with the ReLU bit masks written by the fused forward, against layer-wise fp32 math on the same
@@ -254,7 +257,10 @@ def test_mlp_trunk_bwd_fused(cuda_dev, M, store, monkeypatch):
     warps = default)."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_BWD_STORE", store)
+    monkeypatch.setenv("UPNERF_TRUNK_BWD_STORE", store[0])
+    # default (store path 2): two tiles in flight per CTA; "-single-tile": the one-tile kernel with the same store path
+    monkeypatch.setenv("UPNERF_TRUNK_PP", "0" if store.endswith("single-tile") else "1")
+    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if store.endswith("single-cta") else "2")
     g = torch.Generator(device="cpu").manual_seed(M + 1)
     d = lambda t: t.to(cuda_dev)
     pe = _bf16(torch.randn(M, 64, generator=g))
