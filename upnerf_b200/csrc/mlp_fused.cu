@@ -33,6 +33,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "ptx_sm100.cuh"
 
@@ -104,6 +106,22 @@ __device__ __forceinline__ float softplus_ref(float x) {
   // torch.nn.Softplus(beta=1, threshold=20)
   return x > 20.f ? x : log1pf(expf(x));
 }
+
+// bf16x2 packing of two fp32 values (lo = first argument), plain and with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// ReLU bit masks (relu_mask): one 32-bit word per row and 32-column chunk, two 16-column groups of 16 bits; inside a
+// group the even columns sit in the low byte and the odd columns in the high byte (the order in which the forward
+// epilogue reads them off the packed bf16x2 registers).  Bit of column e (0..15) of a group:
+__host__ __device__ constexpr int relu_mask_bit(int e) { return (e >> 1) + 8 * (e & 1); }
 
 // Copy-out of one finished 128 x 64 bf16 box (the dedicated copy-out warps, lsu_store == 2).  A warp owns
 // kRowsPer = 128 / kCopyWarps rows: lane -> rows r0 + 4 i (i = 0 .. kRowsPer/4 - 1), 16-byte chunk lane % 8;
@@ -480,8 +498,10 @@ mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_consta
             // one negate + one funnel shift per element
             uint32_t m16 = 0;
 #pragma unroll
-            for (int e = 15; e >= 0; --e)
+            for (int i = 15; i >= 0; --i) {   // bit i of the group <- column e (relu_mask_bit order)
+              const int e = i >= 8 ? 2 * (i - 8) + 1 : 2 * i;
               m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
+            }
             mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
           }
           if (q & 1) {
@@ -792,7 +812,17 @@ mlp_trunk_fwd_pp_kernel(const __grid_constant__ TrunkMaps maps, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (see the single-tile kernel)
+    // ------------------------------------------------------------ epilogue warps
+    // Two sets of eight warps; set s owns the 64-column boxes s and s+2 of every layer, warp (quad, half) handles
+    // rows quad*32.. and the 32-column chunk `half` of a box as two 16-column steps.  With two tiles in flight these
+    // warps are the kernel's bottleneck (ncu: 81 % busy, MMA pipe 40 %), so the per-element path is kept short:
+    //  * layer kinds are compile-time (plain ReLU layer / ReLU + sigma head / final linear): no flag tests inside;
+    //  * ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32) and the ReLU bit mask is read off the PACKED
+    //    result -- x + 0x7fff7fff carries a non-zero 16-bit half into its top bit -- 3 instructions per column
+    //    pair instead of 2 x (max, negate, funnel shift).  Bit order inside a 16-column group: even columns in the
+    //    low byte, odd columns in the high byte (relu_mask_bit(); the backward kernels decode the same way);
+    //  * the bias of the NEXT 16 columns is requested right after the adds that consumed the current one;
+    //  * the mask words leave after the last hand-off (a global store in flight stalls the next proxy fence).
     const int ew = warp - 2;
     const int grp = ew >> 2;
     const int half = grp & 1;
@@ -803,102 +833,112 @@ mlp_trunk_fwd_pp_kernel(const __grid_constant__ TrunkMaps maps, const __grid_con
     const uint32_t sbias = smem_u32(sBias);
     const uint32_t sheadw = smem_u32(sHeadW);
     const uint32_t swz = row & 7;
+    const bool have_mask = args.relu_mask != nullptr;
     uint32_t nst = 0;   // stored layers so far (= releases seen per box and slot)
     int t = 0;
+    // one layer of one slot; kind: 0 = Linear + ReLU, 1 = Linear + ReLU + share_sigma head, 2 = Linear (final)
+    auto epi = [&](auto kind_c, int l, int x, int unit, uint32_t lay, int store) {
+      constexpr int kKind = decltype(kind_c)::value;
+      constexpr bool kRelu = kKind != 2, kHead = kKind == 1, kFeeds = kKind != 2;
+      const int tile = tile_of(unit, x);
+      const uint32_t sact_row = smem_u32(sAct) + x * kActBytes + row * 128;
+      const uint32_t bias_l = sbias + l * 1024;
+      mbar_wait(&bar_tfull[x], lay & 1);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + x * 256;
+      uint32_t mw[2] = {0, 0};
+      float hacc = 0.f;
+      uint32_t r[2][16];
+      tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
+      float4 b4[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b4[k] = lds128(bias_l + (set * 64 + half * 32 + k * 4) * 4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int box = set + (q & 2);
+        const int col0 = box * 64 + half * 32 + (q & 1) * 16;
+        // the previous contents of this box must have been copied out before my first write
+        if ((q & 1) == 0 && nst) mbar_wait(&bar_stfree[x * 4 + box], (nst - 1) & 1);
+        tmem_ld_wait_dep(r[q & 1]);
+        const uint32_t* rr = r[q & 1];
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[k * 4 + 0] = __uint_as_float(rr[k * 4 + 0]) + b4[k].x;
+          v[k * 4 + 1] = __uint_as_float(rr[k * 4 + 1]) + b4[k].y;
+          v[k * 4 + 2] = __uint_as_float(rr[k * 4 + 2]) + b4[k].z;
+          v[k * 4 + 3] = __uint_as_float(rr[k * 4 + 3]) + b4[k].w;
+        }
+        if (q < 3) {
+          const int ncol0 = (set + ((q + 1) & 2)) * 64 + half * 32 + ((q + 1) & 1) * 16;
+          tmem_ld_32x16(taddr + ncol0, r[(q + 1) & 1]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) b4[k] = lds128(bias_l + (ncol0 + k * 4) * 4);
+        } else {
+          // my last read of this accumulator is in registers: the MMAs of this slot's next layer may overwrite it
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane0) mbar_arrive(&bar_tempty[x]);
+        }
+        uint32_t o[8];
+        if (kHead) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 w4 = lds128(sheadw + (col0 + k * 4) * 4);
+            hacc += v[k * 4] * w4.x + v[k * 4 + 1] * w4.y + v[k * 4 + 2] * w4.z + v[k * 4 + 3] * w4.w;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (kRelu && !kHead) ? pack_bf16x2_relu(v[2 * e], v[2 * e + 1]) : pack_bf16x2(v[2 * e], v[2 * e + 1]);
+        const uint32_t box_row = sact_row + box * kBoxBytes;
+        const uint32_t s0 = half * 4 + (q & 1) * 2;
+        sts128(box_row + ((s0 ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+        sts128(box_row + (((s0 + 1) ^ swz) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+        if (kRelu && have_mask) {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = (acc >> 1) | ((o[e] + 0x7fff7fffu) & 0x80008000u);
+          const uint32_t m16 = ((acc >> 16) & 0xff00u) | ((acc >> 8) & 0xffu);
+          mw[q >> 1] = (q & 1) ? (mw[q >> 1] | (m16 << 16)) : m16;
+        }
+        if (q & 1) {
+          fence_proxy_async_smem();   // my writes -> visible to the async proxy (the next layer's MMAs)
+          if (kFeeds) {
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane0) mbar_arrive(&bar_act[x * 4 + box]);
+          }
+          if (store) {
+            __syncwarp();
+            if (lane0) mbar_arrive(&bar_st[x * 4 + box]);
+          }
+        }
+      }
+      if (kRelu && have_mask) {
+        uint32_t* mrow = args.relu_mask + ((static_cast<int64_t>(tile) * 8 + l) * 8 + half) * kTileM + row;
+        mrow[(set * 2) * kTileM] = mw[0];
+        mrow[((set + 2) * 2) * kTileM] = mw[1];
+      }
+      if (kHead) {
+        const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
+        sHead[grp * kTileM + row] = hacc;
+        named_bar_sync(4, kEpiThreads);
+        if (grp == 0 && grow < args.M)
+          args.head_out[grow] = softplus_ref(sHead[row] + sHead[kTileM + row] + sHead[2 * kTileM + row] +
+                                             sHead[3 * kTileM + row] + args.head_b[0]);
+        named_bar_sync(4, kEpiThreads);   // the other slot's partial sums follow in the same buffer
+      }
+    };
     for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
       for (int l = 0; l < kNL; ++l) {
-        const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
         const int store = args.layer[l].store;
         const uint32_t lay = static_cast<uint32_t>(t * kNL + l);
-        const bool want_mask = relu && args.relu_mask != nullptr;
         for (int x = 0; x < 2; ++x) {
-          const int tile = tile_of(unit, x);
-          const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
-          const uint32_t sact_row = smem_u32(sAct) + x * kActBytes + row * 128;
-          mbar_wait(&bar_tfull[x], lay & 1);
-          tc_fence_after_sync();
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + x * 256;
-          uint32_t mbits = 0;
-          float hacc = 0.f;
-          uint32_t r[2][16];
-          tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int box = set + (q & 2);
-            const int col0 = box * 64 + half * 32 + (q & 1) * 16;
-            // the previous contents of this box must have been copied out before my first write
-            if ((q & 1) == 0 && nst) mbar_wait(&bar_stfree[x * 4 + box], (nst - 1) & 1);
-            float4 b4[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) b4[k] = lds128(sbias + (l * 256 + col0 + k * 4) * 4);
-            tmem_ld_wait_dep(r[q & 1]);
-            const uint32_t* rr = r[q & 1];
-            float v[16];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              v[k * 4 + 0] = __uint_as_float(rr[k * 4 + 0]) + b4[k].x;
-              v[k * 4 + 1] = __uint_as_float(rr[k * 4 + 1]) + b4[k].y;
-              v[k * 4 + 2] = __uint_as_float(rr[k * 4 + 2]) + b4[k].z;
-              v[k * 4 + 3] = __uint_as_float(rr[k * 4 + 3]) + b4[k].w;
-            }
-            if (q < 3) {
-              const int nbox = set + ((q + 1) & 2);
-              tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
-            } else {
-              // my last read of this accumulator is in registers: the MMAs of this slot's next layer may overwrite it
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_tempty[x]);
-            }
-            if (relu) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            if (head) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 w4 = lds128(sheadw + (col0 + k * 4) * 4);
-                hacc += v[k * 4] * w4.x + v[k * 4 + 1] * w4.y + v[k * 4 + 2] * w4.z + v[k * 4 + 3] * w4.w;
-              }
-            }
-            uint4 o[2];
-            __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            const uint32_t box_row = sact_row + box * kBoxBytes;
-            const uint32_t s0 = half * 4 + (q & 1) * 2;
-            sts128(box_row + ((s0 ^ swz) << 4), o[0]);
-            sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
-            if (want_mask) {
-              uint32_t m16 = 0;
-#pragma unroll
-              for (int e = 15; e >= 0; --e)
-                m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
-              mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
-            }
-            if (q & 1) {
-              fence_proxy_async_smem();   // my writes -> visible to the async proxy (the next layer's MMAs)
-              if (feeds) {
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane0) mbar_arrive(&bar_act[x * 4 + box]);
-              }
-              if (want_mask)
-                args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
-              if (store) {
-                __syncwarp();
-                if (lane0) mbar_arrive(&bar_st[x * 4 + box]);
-              }
-            }
-          }
-          if (head) {
-            sHead[grp * kTileM + row] = hacc;
-            named_bar_sync(4, kEpiThreads);
-            if (grp == 0 && grow < args.M)
-              args.head_out[grow] = softplus_ref(sHead[row] + sHead[kTileM + row] + sHead[2 * kTileM + row] +
-                                                 sHead[3 * kTileM + row] + args.head_b[0]);
-            named_bar_sync(4, kEpiThreads);   // slot B's partial sums follow in the same buffer
-          }
+          if (l < 7) epi(std::integral_constant<int, 0>{}, l, x, unit, lay, store);
+          else if (l == 7) epi(std::integral_constant<int, 1>{}, l, x, unit, lay, store);
+          else epi(std::integral_constant<int, 2>{}, l, x, unit, lay, store);
         }
         if (store) ++nst;
       }
@@ -1190,7 +1230,7 @@ mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant
             }
           }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = ((m16 >> e) & 1u) ? v[e] : 0.f;
+          for (int e = 0; e < 16; ++e) v[e] = ((m16 >> relu_mask_bit(e)) & 1u) ? v[e] : 0.f;
           uint4 o[2];
           __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
@@ -1511,7 +1551,7 @@ mlp_trunk_bwd_pp_kernel(const __grid_constant__ bwd::BwdMaps maps, const __grid_
               }
             }
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = ((m16 >> e) & 1u) ? v[e] : 0.f;
+            for (int e = 0; e < 16; ++e) v[e] = ((m16 >> relu_mask_bit(e)) & 1u) ? v[e] : 0.f;
             uint4 o[2];
             __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
