@@ -31,22 +31,22 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;            // ring depth = min(kMaxStages, kStageBoxes / boxes per stage): 4 at K = 256
+constexpr int kStageBoxes = 27;          // shared memory given to the operand ring, in 8 KB boxes
 constexpr int kBS = 64;                 // samples per stage
 constexpr int kBoxBytes = kBS * 128;    // one 64-sample x 64-column bf16 box
 constexpr int kABoxes = 2;              // 128 output rows
 constexpr int kMaxBBoxes = 5;           // K <= 320
-constexpr int kStageBytes = (kABoxes + kMaxBBoxes) * kBoxBytes;
 constexpr int kOnesBytes = 1024;
 constexpr int kMaxK = 320;
 constexpr int kBiasCol = 384;           // TMEM column of the bias-gradient accumulator
 constexpr int kThreads = 192;
 
 constexpr int kOffStage = 0;
-constexpr int kOffOnes = kOffStage + kStages * kStageBytes;
+constexpr int kOffOnes = kOffStage + kStageBoxes * kBoxBytes;
 constexpr int kOffMap = kOffOnes + kOnesBytes;
 constexpr int kOffBar = kOffMap + kMaxK * 4;
-constexpr int kNumBars = 2 * kStages + 1;
+constexpr int kNumBars = 2 * kMaxStages + 1;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;
 
@@ -97,8 +97,8 @@ wgrad_tc_kernel(const __grid_constant__ WgradGroupParams grp) {
   int* sMap = reinterpret_cast<int*>(smem + kOffMap);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + kStages;
-  uint64_t* bar_done = bars + 2 * kStages;
+  uint64_t* bar_empty = bars + kMaxStages;
+  uint64_t* bar_done = bars + 2 * kMaxStages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -107,6 +107,9 @@ wgrad_tc_kernel(const __grid_constant__ WgradGroupParams grp) {
   const int split = local / args.chunks;
   const int K = args.K;
   const int bboxes = K / 64;
+  // ring geometry of THIS problem: a stage holds 64 samples of both operands
+  const int kStageBytes = (kABoxes + bboxes) * kBoxBytes;
+  const int kStages = kStageBoxes / (kABoxes + bboxes) < kMaxStages ? kStageBoxes / (kABoxes + bboxes) : kMaxStages;
 
   const int64_t row_begin = static_cast<int64_t>(split) * args.rows_per_split;
   int64_t row_end = row_begin + args.rows_per_split;
@@ -116,7 +119,7 @@ wgrad_tc_kernel(const __grid_constant__ WgradGroupParams grp) {
   if (warp == 0 && lane == 0) {
     prefetch_tmap(tmY);
     prefetch_tmap(tmX);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
