@@ -30,11 +30,12 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;      // ring depth = min(kMaxStages, kRingBytes / stage bytes): 3 at N = 256, 4 at 128, 6 at 64
 constexpr int kBM = 128;          // rows per tile (UMMA M)
 constexpr int kBK = 64;           // K elements per stage = one 128-byte swizzle span
 constexpr int kABytes = kBM * 128;
 constexpr int kBBytesMax = 256 * 128;
+constexpr int kRingBytes = 3 * (kBM * 128 + kBBytesMax);   // operand ring: a stage is [A 128 x 64 | B N x 64]
 constexpr int kCBytes = kBM * 128;  // one 128 x 64 bf16 output box
 constexpr int kGroups = 4;          // epilogue warp groups (one C box each)
 constexpr int kEpiThreads = kGroups * 128;
@@ -43,14 +44,13 @@ constexpr int kMaxN = 256;
 constexpr int kMaxHeads = 3;
 
 constexpr int kOffA = 0;
-constexpr int kOffB = kOffA + kStages * kABytes;
-constexpr int kOffC = kOffB + kStages * kBBytesMax;
+constexpr int kOffC = kOffA + kRingBytes;
 constexpr int kOffVec = kOffC + kGroups * kCBytes;
 constexpr int kVecFloats = kMaxN * (2 + kMaxHeads);
 constexpr int kOffHead = kOffVec + kVecFloats * 4;
 constexpr int kHeadFloats = 2 * kGroups * kBM * kMaxHeads;   // [acc][group][row][head]
 constexpr int kOffBar = kOffHead + kHeadFloats * 4;
-constexpr int kNumBars = 2 * kStages + 4 + kGroups;
+constexpr int kNumBars = 2 * kMaxStages + 4 + kGroups;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + slack for manual 1024-byte alignment
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -88,16 +88,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* sA = smem + kOffA;
-  uint8_t* sB = smem + kOffB;
   uint8_t* sC = smem + kOffC;
   float* sVec = reinterpret_cast<float*>(smem + kOffVec);
   float* sHead = reinterpret_cast<float*>(smem + kOffHead);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + kStages;
-  uint64_t* bar_tfull = bars + 2 * kStages;
-  uint64_t* bar_tempty = bars + 2 * kStages + 2;
-  uint64_t* bar_aux = bars + 2 * kStages + 4;
+  uint64_t* bar_empty = bars + kMaxStages;
+  uint64_t* bar_tfull = bars + 2 * kMaxStages;
+  uint64_t* bar_tempty = bars + 2 * kMaxStages + 2;
+  uint64_t* bar_aux = bars + 2 * kMaxStages + 4;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -106,6 +105,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks = args.K / kBK;
   const int nchunks = N / 64;
   const bool has_aux = args.ep.aux_mode != 0;
+  // ring geometry of THIS layer: the narrower B is, the more A (the HBM stream) is in flight
+  const int kStageBytes = kABytes + N * 128;
+  const int kStages = kRingBytes / kStageBytes < kMaxStages ? kRingBytes / kStageBytes : kMaxStages;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -113,7 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     if (has_aux) prefetch_tmap(&tmAux);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
@@ -150,9 +152,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&bar_full[stage], tx);
-          if (kb < args.kb1) tma_load_2d(sA + stage * kABytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
-          else tma_load_2d(sA + stage * kABytes, &tmA2, &bar_full[stage], (kb - args.kb1) * kBK, tile * kBM);
-          tma_load_2d(sB + stage * kBBytesMax, &tmB, &bar_full[stage], kb * kBK, 0);
+          if (kb < args.kb1) tma_load_2d(sA + stage * kStageBytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
+          else tma_load_2d(sA + stage * kStageBytes, &tmA2, &bar_full[stage], (kb - args.kb1) * kBK, tile * kBM);
+          tma_load_2d(sA + stage * kStageBytes + kABytes, &tmB, &bar_full[stage], kb * kBK, 0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -175,8 +177,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(sB + stage * kBBytesMax);
+          const uint32_t a_addr = smem_u32(sA + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
