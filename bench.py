@@ -438,11 +438,11 @@ def run_train(args):
     roofline = hbm_view("wgrad_tc", "wgrad_tc_kernel")
     all_tc = ["gemm_tc", "wgrad_tc", "trunk_fwd", "trunk_bwd", "tnet", "gemm_tf32"]
     roofline_mlp = {
-        "fused_trunk": tensor_view(["trunk_fwd", "trunk_bwd"], "mlp_trunk_fwd_kernel + mlp_trunk_bwd_kernel"),
-        "fused_trunk_fwd": tensor_view(["trunk_fwd"], "mlp_trunk_fwd_kernel"),
-        "fused_trunk_bwd": tensor_view(["trunk_bwd"], "mlp_trunk_bwd_kernel"),
-        "fused_trunk_hbm": {c: hbm_view(c, k) for c, k in (("trunk_fwd", "mlp_trunk_fwd_kernel"),
-                                                            ("trunk_bwd", "mlp_trunk_bwd_kernel"))},
+        "fused_trunk": tensor_view(["trunk_fwd", "trunk_bwd"], "pp::mlp_trunk_fwd_pp_kernel + pp::mlp_trunk_bwd_pp_kernel"),
+        "fused_trunk_fwd": tensor_view(["trunk_fwd"], "pp::mlp_trunk_fwd_pp_kernel"),
+        "fused_trunk_bwd": tensor_view(["trunk_bwd"], "pp::mlp_trunk_bwd_pp_kernel"),
+        "fused_trunk_hbm": {c: hbm_view(c, k) for c, k in (("trunk_fwd", "pp::mlp_trunk_fwd_pp_kernel"),
+                                                            ("trunk_bwd", "pp::mlp_trunk_bwd_pp_kernel"))},
         "gemm_tc_hbm": hbm_view("gemm_tc", "gemm_tc_kernel"),
         "all_tcgen05": tensor_view(all_tc, "all tcgen05 kernels (fused trunk, layer GEMMs, weight gradients)"),
         "whole_step_algorithmic": {"flop_per_ray": FLOP_PER_RAY, "tflops": value / world * FLOP_PER_RAY / 1e12,
@@ -567,7 +567,7 @@ def run_render(args):
     hbm_view, tensor_view = roofline_views(prof, pk)
     total_rays = RENDER_W * RENDER_H
     value = total_rays / (ms * 1e-3)
-    roofline = tensor_view(["trunk_fwd"], "mlp_trunk_fwd_kernel (forward-only: activations stay on chip)")
+    roofline = tensor_view(["trunk_fwd"], "pp::mlp_trunk_fwd_pp_kernel (forward-only: activations stay on chip)")
     line = {
         "metric": RENDER_METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

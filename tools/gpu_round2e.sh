@@ -16,6 +16,7 @@ timeout -s KILL 300 python tools/bench_hbm.py > gpurun_out/${T}_hbm.jsonl 2> gpu
 timeout -s KILL 300 python tools/bench_gemm.py > gpurun_out/${T}_gemm.txt 2>&1
 timeout -s KILL 120 python tools/bench_gemm.py epi > gpurun_out/${T}_gemm_epi.txt 2>&1
 timeout -s KILL 120 python tools/bench_gemm.py tf32 > gpurun_out/${T}_gemm_tf32.txt 2>&1
+timeout -s KILL 200 python tools/trunk_variants.py > gpurun_out/${T}_trunk_variants.txt 2>&1
 # launch list of the bench command (eager warm-up steps + graph replays; per-launch times are cold-cache and serialised)
 timeout -s KILL 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_launch.log 2>&1
 python tools/launch_summary.py gpurun_out/${T}_launches.csv 50 > gpurun_out/${T}_launches_summary.txt 2>&1
