@@ -30,12 +30,13 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kMaxStages = 8;      // ring depth = min(kMaxStages, kRingBytes / stage bytes): 3 at N = 256, 4 at 128, 6 at 64
+constexpr int kMaxStages = 8;      // A ring depth = min(kMaxStages, what the B ring leaves of kRingBytes): 5 at N = 256, 7 at 128, 8 at 64
+constexpr int kBStages = 4;        // B (the layer's weights) comes from L2: 64 KB of stages (2 at N = 256, 4 below) cover its latency
 constexpr int kBM = 128;          // rows per tile (UMMA M)
 constexpr int kBK = 64;           // K elements per stage = one 128-byte swizzle span
 constexpr int kABytes = kBM * 128;
 constexpr int kBBytesMax = 256 * 128;
-constexpr int kRingBytes = 3 * (kBM * 128 + kBBytesMax);   // operand ring: a stage is [A 128 x 64 | B N x 64]
+constexpr int kRingBytes = 3 * (kBM * 128 + kBBytesMax);   // operand area: [B ring: 2 x (N x 64)] [A ring: n x (128 x 64)]
 constexpr int kCBytes = kBM * 128;  // one 128 x 64 bf16 output box
 constexpr int kGroups = 4;          // epilogue warp groups (one C box each)
 constexpr int kEpiThreads = kGroups * 128;
@@ -50,7 +51,7 @@ constexpr int kVecFloats = kMaxN * (2 + kMaxHeads);
 constexpr int kOffHead = kOffVec + kVecFloats * 4;
 constexpr int kHeadFloats = 2 * kGroups * kBM * kMaxHeads;   // [acc][group][row][head]
 constexpr int kOffBar = kOffHead + kHeadFloats * 4;
-constexpr int kNumBars = 2 * kMaxStages + 4 + kGroups;
+constexpr int kNumBars = 2 * kMaxStages + 2 * kBStages + 4 + kGroups;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmem + 16 + 1024;  // + slack for manual 1024-byte alignment
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -92,11 +93,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* sVec = reinterpret_cast<float*>(smem + kOffVec);
   float* sHead = reinterpret_cast<float*>(smem + kOffHead);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + kMaxStages;
-  uint64_t* bar_tfull = bars + 2 * kMaxStages;
-  uint64_t* bar_tempty = bars + 2 * kMaxStages + 2;
-  uint64_t* bar_aux = bars + 2 * kMaxStages + 4;
+  uint64_t* bar_full = bars;                       // A stage landed
+  uint64_t* bar_empty = bars + kMaxStages;         // A stage consumed
+  uint64_t* bar_bfull = bars + 2 * kMaxStages;     // B stage landed
+  uint64_t* bar_bempty = bar_bfull + kBStages;     // B stage consumed
+  uint64_t* bar_tfull = bar_bempty + kBStages;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint64_t* bar_aux = bar_tempty + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -105,9 +108,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kblocks = args.K / kBK;
   const int nchunks = N / 64;
   const bool has_aux = args.ep.aux_mode != 0;
-  // ring geometry of THIS layer: the narrower B is, the more A (the HBM stream) is in flight
-  const int kStageBytes = kABytes + N * 128;
-  const int kStages = kRingBytes / kStageBytes < kMaxStages ? kRingBytes / kStageBytes : kMaxStages;
+  // Ring geometry of THIS layer.  A (activations) streams from HBM, B (the weights, re-read for every tile) from
+  // L2: they have rings of their own so that the HBM stream can run several stages ahead of the short B ring --
+  // with one joint ring a 256-wide layer kept only 3 x 16 KB of A in flight per SM, too little under the step's
+  // HBM contention (the same effect as in wgrad_tc.cu).
+  const int kBStageBytes = N * 128;
+  const int nB = 65536 / kBStageBytes < kBStages ? 65536 / kBStageBytes : kBStages;   // B ring depth of this layer
+  uint8_t* sB = sA;                                           // B ring first
+  uint8_t* sAr = sA + nB * kBStageBytes;                      // then the A ring
+  const int a_room = (kRingBytes - nB * kBStageBytes) / kABytes;
+  const int kStages = a_room < kMaxStages ? a_room : kMaxStages;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -118,6 +128,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
+    }
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&bar_bfull[i], 1);
+      mbar_init(&bar_bempty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_tfull[i], 1);
@@ -145,19 +159,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = kABytes + N * 128;
-      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], tx);
-          if (kb < args.kb1) tma_load_2d(sA + stage * kStageBytes, &tmA, &bar_full[stage], kb * kBK, tile * kBM);
-          else tma_load_2d(sA + stage * kStageBytes, &tmA2, &bar_full[stage], (kb - args.kb1) * kBK, tile * kBM);
-          tma_load_2d(sA + stage * kStageBytes + kABytes, &tmB, &bar_full[stage], kb * kBK, 0);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+      // one thread issues both streams in order; the A load of K-block j is issued `skew` blocks before the B
+      // load of the same block, so A runs ahead by up to its whole ring while B stays two stages deep
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x) ++my_tiles;
+      const int total = my_tiles * kblocks;
+      const int skew = kStages - nB > 0 ? kStages - nB : 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int a_tile = blockIdx.x, a_kb = 0, b_kb = 0;
+      for (int j = 0; j < total + skew; ++j) {
+        if (j < total) {
+          mbar_wait(&bar_empty[sa], pha ^ 1);
+          mbar_arrive_expect_tx(&bar_full[sa], kABytes);
+          if (a_kb < args.kb1) tma_load_2d(sAr + sa * kABytes, &tmA, &bar_full[sa], a_kb * kBK, a_tile * kBM);
+          else tma_load_2d(sAr + sa * kABytes, &tmA2, &bar_full[sa], (a_kb - args.kb1) * kBK, a_tile * kBM);
+          if (++a_kb == kblocks) {
+            a_kb = 0;
+            a_tile += gridDim.x;
+          }
+          if (++sa == kStages) {
+            sa = 0;
+            pha ^= 1;
+          }
+        }
+        if (j >= skew) {
+          mbar_wait(&bar_bempty[sb], phb ^ 1);
+          mbar_arrive_expect_tx(&bar_bfull[sb], kBStageBytes);
+          tma_load_2d(sB + sb * kBStageBytes, &tmB, &bar_bfull[sb], b_kb * kBK, 0);
+          if (++b_kb == kblocks) b_kb = 0;
+          if (++sb == nB) {
+            sb = 0;
+            phb ^= 1;
           }
         }
       }
@@ -166,8 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kBM, N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
       int t = 0;
       for (int tile = blockIdx.x; tile < args.num_tiles; tile += gridDim.x, ++t) {
         const int acc = t & 1;
@@ -175,20 +208,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&bar_full[stage], phase);
+          mbar_wait(&bar_full[sa], pha);
+          mbar_wait(&bar_bfull[sb], phb);
           tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + stage * kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_addr = smem_u32(sAr + sa * kABytes);
+          const uint32_t b_addr = smem_u32(sB + sb * kBStageBytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
             const uint64_t db = umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128);
             mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          mma_commit(&bar_empty[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+          mma_commit(&bar_empty[sa]);    // both stages are free when these MMAs retire
+          mma_commit(&bar_bempty[sb]);
+          if (++sa == kStages) {
+            sa = 0;
+            pha ^= 1;
+          }
+          if (++sb == nB) {
+            sb = 0;
+            phb ^= 1;
           }
         }
         mma_commit(&bar_tfull[acc]);  // accumulator complete -> epilogue
