@@ -203,21 +203,16 @@ def _trunk_reference(pe, ws, bs, sw, sb):
     return outs, sig
 
 
-@pytest.mark.parametrize("variant", ["multicast", "single-cta", "multicast-tma-store", "multicast-epilogue-copy",
-                                     "multicast-single-tile", "single-cta-single-tile"])
+@pytest.mark.parametrize("variant", ["multicast", "single-cta"])
 @pytest.mark.parametrize("M", [128, 128 * 3 + 37, 128 * 148 * 2 + 128 * 5 + 1, 128 * 148 * 5 + 77])
 def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused trunk (PE -> 8 layers + skip -> final, sigma head) vs the layer-wise reference;
-    covers a single tile, a ragged last tile and several units per CTA pair (pipeline wrap-around), for the
-    default kernel (two tiles in flight per CTA, CTA pairs sharing the weight stream by multicast), the same with
-    single CTAs (UPNERF_TRUNK_CLUSTER=1), and the one-tile-per-CTA kernel with its three activation store paths."""
+    covers a single tile, a ragged last tile, dummy tiles of an incomplete unit and several units per CTA pair
+    (pipeline wrap-around), for CTA pairs sharing the weight stream by multicast (default) and single CTAs
+    (UPNERF_TRUNK_CLUSTER=1)."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant.startswith("single-cta") else "2")
-    # default: two tiles in flight per CTA; "-single-tile" (and every store path but the copy-out warps): one tile
-    monkeypatch.setenv("UPNERF_TRUNK_PP", "0" if variant.endswith("single-tile") else "1")
-    # activation store path: 2 = copy-out warps (default), 0 = TMA stores, 1 = epilogue copy (both single-tile only)
-    monkeypatch.setenv("UPNERF_TRUNK_LSU_STORE", {"multicast-tma-store": "0", "multicast-epilogue-copy": "1"}.get(variant, "2"))
+    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant == "single-cta" else "2")
 
     g = torch.Generator(device="cpu").manual_seed(M)
     pe = _bf16(torch.randn(M, 64, generator=g))
@@ -247,20 +242,16 @@ def test_mlp_trunk_fwd_fused(cuda_dev, M, variant, monkeypatch):
     assert torch.allclose(sig, ref_sig, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("store", ["0", "1", "2", "2-single-tile", "2-single-cta"])
+@pytest.mark.parametrize("variant", ["multicast", "single-cta"])
 @pytest.mark.parametrize("M", [128 * 2 + 77, 128 * 148 * 2 + 128 * 3 + 9, 128 * 148 * 5 + 77])
-def test_mlp_trunk_bwd_fused(cuda_dev, M, store, monkeypatch):
+def test_mlp_trunk_bwd_fused(cuda_dev, M, variant, monkeypatch):
     """Fused backward chain: dY8 = (dHF W_F + dssig (x) w_s) * [H8>0], dYl = (dY(l+1) W(l+1)) * [Hl>0],
     with the ReLU bit masks written by the fused forward, against layer-wise fp32 math on the same
-    bf16 operands (masks taken from the forward kernel's own activations, so no mask can flip); for the three
-    activation store paths of the kernel (UPNERF_TRUNK_BWD_STORE: 0 TMA stores, 1 epilogue copy, 2 copy-out
-    warps = default)."""
+    bf16 operands (masks taken from the forward kernel's own activations, so no mask can flip); CTA pairs and
+    single CTAs (UPNERF_TRUNK_CLUSTER=1)."""
     from upnerf_b200 import _lib as L
 
-    monkeypatch.setenv("UPNERF_TRUNK_BWD_STORE", store[0])
-    # default (store path 2): two tiles in flight per CTA; "-single-tile": the one-tile kernel with the same store path
-    monkeypatch.setenv("UPNERF_TRUNK_PP", "0" if store.endswith("single-tile") else "1")
-    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if store.endswith("single-cta") else "2")
+    monkeypatch.setenv("UPNERF_TRUNK_CLUSTER", "1" if variant == "single-cta" else "2")
     g = torch.Generator(device="cpu").manual_seed(M + 1)
     d = lambda t: t.to(cuda_dev)
     pe = _bf16(torch.randn(M, 64, generator=g))

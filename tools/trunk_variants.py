@@ -1,4 +1,4 @@
-"""Timing A/B of the fused trunk kernels (two tiles in flight vs one, store paths) in one process (CUDA events, M = 786k).
+"""Timing A/B of the fused trunk kernels (CTA pairs vs single CTAs, masks on / off) in one process (CUDA events, M = 786k).
 usage: python tools/trunk_variants.py [NAME=ENV1:VAL,ENV2:VAL ...]   (default: a fixed list of variants)"""
 import os
 import sys
@@ -11,14 +11,11 @@ from upnerf_b200 import _lib as L
 from tools.bench_gemm import timeit
 
 VARIANTS = [
-    ("default (two tiles in flight)", {}),
-    ("single tile", {"UPNERF_TRUNK_PP": "0"}),
-    ("two tiles, no mask", {"TV_NOMASK": "1"}),
-    ("single tile, no mask", {"UPNERF_TRUNK_PP": "0", "TV_NOMASK": "1"}),
-    ("single tile, TMA stores", {"UPNERF_TRUNK_LSU_STORE": "0", "UPNERF_TRUNK_BWD_STORE": "0"}),
-    ("single tile, epilogue copy", {"UPNERF_TRUNK_LSU_STORE": "1", "UPNERF_TRUNK_BWD_STORE": "1"}),
+    ("CTA pairs (default)", {}),
+    ("single CTAs", {"UPNERF_TRUNK_CLUSTER": "1"}),
+    ("CTA pairs, no masks", {"TV_NOMASK": "1"}),
 ]
-KEYS = ("TV_NOMASK", "UPNERF_TRUNK_PP", "UPNERF_TRUNK_LSU_STORE", "UPNERF_TRUNK_BWD_STORE")
+KEYS = ("TV_NOMASK", "UPNERF_TRUNK_CLUSTER")
 
 
 def main():

@@ -1,34 +1,30 @@
-// Fused NeRF trunk on tcgen05 -- upnerf_mlp_trunk_fwd_bf16.
+// Fused NeRF trunk on tcgen05 -- upnerf_mlp_trunk_fwd_bf16 / upnerf_mlp_trunk_bwd_bf16.
 //
 // One persistent kernel evaluates, per 128-sample tile, the whole xyz trunk of NeRF.forward
 // (reference models/nerf.py:84-93): PE -> 8 x (Linear 256 + ReLU) with the skip concat at
-// layer 5 -> xyz_encoding_final, plus the share_sigma row-dot + Softplus (:89).  Activations
-// never leave the SM between layers: the epilogue of layer l writes bf16 straight into the
-// 128-byte-swizzled K-major shared-memory boxes that layer l+1's MMAs read as their A operand.
-// Every layer output is also TMA-stored to HBM once (write-only) because backward needs it.
+// layer 5 -> xyz_encoding_final, plus the share_sigma row-dot + Softplus (:89); a second one runs the
+// data-gradient chain of the same layers.  Activations never leave the SM between layers: the epilogue
+// of layer l writes bf16 straight into the 128-byte-swizzled K-major shared-memory boxes that layer
+// l+1's MMAs read as their A operand.  Every layer output also goes to HBM once (write-only) because
+// the weight gradients need it.
 //
-//   warp 0      TMA producer: streams the layer weights (256 x 64 bf16 K-chunks, 3 stages)
-//               from L2 and the PE tile of the current / next sample tile.
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x 256 x 16).
+//   warp 0      TMA producer: streams the layer weights (N-halves of 64-column K-chunks, 16 KB stages)
+//               from L2 -- CTA pairs share the stream by multicast -- and the input tiles of the two slots.
+//   warp 1      TMEM allocator + warp-uniform tcgen05.mma issuer (UMMA 128 x 128 x 16, one elected lane).
 //   warps 2..17 epilogue, two sets of eight warps (set s owns output boxes s and s+2):
 //               thread = one output row x 16 of the 32 columns of a chunk.
-//   warps 18,19 copy-out (default store path): wait for "box written", read their 64 rows of the
-//               swizzled box and stream them to HBM with coalesced 16-byte st.global.
+//   warps 18,19 copy-out: wait for "box written", read their 64 rows of the swizzled box and stream
+//               them to HBM with coalesced 16-byte st.global.
 //
-// Pipelining inside a tile: the accumulator is double buffered in TMEM (2 x 256 columns), and
-// the epilogue releases its output box by box (64 columns, one mbarrier each), so the MMAs of
-// layer l+1 over K-box b start as soon as box b of layer l has been written -- the tensor pipe
-// only idles for the first box of each layer.  Layers whose first K-chunk is the PE tile
-// (layer 1 and the skip layer) start even earlier, during the previous layer's epilogue.
+// Two tiles are in flight per CTA (slots A and B, strictly alternating MMA A(l) B(l) A(l+1) ... /
+// epilogue A(l) B(l) ...), so one tile's hand-offs and epilogue run under the other tile's MMAs; inside a
+// tile the epilogue releases its output box by box (64 columns, one mbarrier each), so the MMAs of layer
+// l+1 over K-box b can start as soon as box b of layer l has been written.
 //
-// Measured (B200, M = 786432): 1.19 ms = 738 TFLOP/s with the activation stores, 0.79 ms
-// (1107 TFLOP/s) with the stores disabled.  ncu (profiles/r1_trunk_ncu_full.txt): tensor pipe active
-// 35 %, shared-memory pipes 26 % + 26 %, DRAM 38 %, issue slots 31 % -- no unit is saturated; the
-// kernel is bound by the serial MMA -> epilogue -> MMA chain of a tile (the MMAs of a layer-tile
-// take 2048 cycles of a ~5500-cycle period).  Tried and measured, none faster: a dedicated store
-// warp (epilogue never waits for a store to drain: 1.21 ms), per-thread st.global of the outputs
-// (1.84 ms), the cta_group::2 pair MMA (1.42 ms).  The fix is two tiles in flight per CTA so one
-// tile's epilogue runs under the other's MMAs; see DESIGN.md section 5.
+// History and measurements (one tile per CTA with double-buffered accumulators, TMA-store and
+// epilogue-copy store paths, cta_group::2 pair MMAs, the deletion profile that showed the ~3600-cycle
+// MMA -> epilogue -> MMA round trip, and why none of it moves the wall time: the kernels run under the
+// board's power cap): DESIGN.md section 5, profiles/r2_trunk_study.md, `git log -- upnerf_b200/csrc/mlp_fused.cu`.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,43 +40,22 @@ namespace {
 using namespace ptx;
 
 constexpr int kNL = UPNERF_TRUNK_LAYERS;  // 8 trunk layers + xyz_encoding_final
-constexpr int kWStages = 3;
 constexpr int kTileM = 128;
 constexpr int kBoxBytes = kTileM * 128;   // 128 rows x 64 bf16 columns
 constexpr int kActBytes = 4 * kBoxBytes;  // 128 x 256 activation tile
-constexpr int kWBytes = 256 * 128;        // 256 output features x 64 K columns
-constexpr int kSetThreads = 256;           // one epilogue set: 8 warps
-constexpr int kEpiThreads = 2 * kSetThreads;
-constexpr int kThreads = 64 + kEpiThreads;
-constexpr int kCopyWarps = 2;                       // forward, lsu_store == 2: dedicated copy-out warps
-constexpr int kThreadsF = kThreads + 32 * kCopyWarps;
-constexpr int kChunks = 8;                // 32-column chunks per 256-wide layer
-
-constexpr int kOffAct = 0;
-constexpr int kOffPE = kOffAct + kActBytes;
-constexpr int kOffW = kOffPE + 2 * kBoxBytes;
-constexpr int kOffBias = kOffW + kWStages * kWBytes;
-constexpr int kOffHeadW = kOffBias + kNL * 256 * 4;
-constexpr int kOffHead = kOffHeadW + 256 * 4;
-constexpr int kOffBar = kOffHead + 4 * kTileM * 4;
-constexpr int kMaxWStages = kWStages;
-constexpr int kNumBars = 2 * kMaxWStages + 4 + kChunks + 2 + 8;
-constexpr int kOffTmem = kOffBar + kNumBars * 8;
-constexpr int kSmemBytes = kOffTmem + 16 + 1024;
-static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+constexpr int kEpiThreads = 512;          // two epilogue sets of eight warps
+constexpr int kCopyWarps = 2;             // dedicated copy-out warps
+constexpr int kThreadsF = 64 + kEpiThreads + 32 * kCopyWarps;
 
 struct LayerDesc {
   int w_act;    // first K column (in Wcat) of the weights multiplying the activation tile; -1: none
   int w_pe;     // K column of the weights multiplying the PE tile; -1: none
-  int relu;
-  int feeds;    // output is the A operand of the next layer
-  int head;     // share_sigma rides on this layer's epilogue
   int pe_last;  // last user of the PE tile within a sample tile
   int store;    // keep this layer's output in HBM (backward needs it; inference does not)
 };
 
 struct TrunkMaps {
-  CUtensorMap w, pe, out[kNL];
+  CUtensorMap w, pe;
 };
 
 struct TrunkArgs {
@@ -92,12 +67,6 @@ struct TrunkArgs {
   const float* head_b;
   float* head_out;
   uint32_t* relu_mask;  // [tiles][8 layers][8 chunks][128 rows] or nullptr
-  // lsu_store: a finished 64-column box goes to HBM as coalesced 16-byte st.global issued by the
-  // epilogue warps themselves (read back from the swizzled shared-memory box, 8 lanes per 128-byte
-  // row segment) instead of a TMA store.  The TMA unit of an SM moves ~27 B/clk (tools/
-  // tma_store_probe.py); with the weight stream (68 KB per layer and tile) AND the activation
-  // stores (64 KB) on it, it -- not the tensor pipe, shared memory or HBM -- paced the kernel.
-  int lsu_store;   // 0 TMA stores | 1 epilogue copy | 2 copy-out warps
   __nv_bfloat16* out[kNL];
   int64_t ld_out[kNL];
 };
@@ -123,7 +92,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 // epilogue reads them off the packed bf16x2 registers).  Bit of column e (0..15) of a group:
 __host__ __device__ constexpr int relu_mask_bit(int e) { return (e >> 1) + 8 * (e & 1); }
 
-// Copy-out of one finished 128 x 64 bf16 box (the dedicated copy-out warps, lsu_store == 2).  A warp owns
+// Copy-out of one finished 128 x 64 bf16 box (the dedicated copy-out warps).  A warp owns
 // kRowsPer = 128 / kCopyWarps rows: lane -> rows r0 + 4 i (i = 0 .. kRowsPer/4 - 1), 16-byte chunk lane % 8;
 // row r keeps chunk c at slot c ^ (r & 7), and (r & 7) = lane / 8 for even i, lane / 8 + 4 for odd i.
 // The loads of the box are issued eight at a time (immediate offsets off two base registers), the box is
@@ -165,412 +134,12 @@ __device__ __forceinline__ void copy_box_out(uint32_t s_even, uint32_t s_odd, __
   }
 }
 
-// kCluster = 2: the two CTAs of a cluster walk their tiles in lockstep and share the weight
-// stream -- each loads one half (128 output features) of every weight chunk and TMA-multicasts
-// it into both CTAs, which halves the L2 -> shared-memory traffic (the first bound this kernel
-// hits: 1.06 MB of weights per 128-sample tile).
-//
-// (Two tcgen05.mma.cta_group::2 variants of this kernel -- a pair MMA over both CTAs' tiles, and a dual-tile
-// version with two pair tiles in flight -- were built, parity-tested and measured in rounds 1 and 2: 1.42 /
-// 1.27 ms against 1.03-1.09 ms for this one at M = 786k.  They were removed; DESIGN.md section 5 has the numbers.)
-template <int kCluster>
-__global__ void __launch_bounds__(kThreadsF, 1)
-mlp_trunk_fwd_kernel(const __grid_constant__ TrunkMaps maps, const __grid_constant__ TrunkArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sAct = smem + kOffAct;
-  uint8_t* sPE = smem + kOffPE;
-  uint8_t* sW = smem + kOffW;
-  float* sBias = reinterpret_cast<float*>(smem + kOffBias);
-  float* sHeadW = reinterpret_cast<float*>(smem + kOffHeadW);
-  float* sHead = reinterpret_cast<float*>(smem + kOffHead);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  constexpr int kStages = kWStages;
-  constexpr int kStageBytes = kWBytes;
-  uint64_t* bar_wfull = bars;
-  uint64_t* bar_wempty = bars + kMaxWStages;
-  uint64_t* bar_pefull = bars + 2 * kMaxWStages;
-  uint64_t* bar_peempty = bars + 2 * kMaxWStages + 2;
-  uint64_t* bar_act = bars + 2 * kMaxWStages + 4;
-  uint64_t* bar_tfull = bars + 2 * kMaxWStages + 4 + kChunks;
-  uint64_t* bar_st = bar_tfull + 2;        // [4] lsu_store == 2: box written (8 warps of its set) -> copy-out warps
-  uint64_t* bar_stfree = bar_st + 4;       // [4] box copied out (kCopyWarps arrivals) -> may be overwritten
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmem);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  // Tiles are dealt to clusters; CTA r of a cluster takes tile kCluster*unit + r.  Every CTA of a
-  // cluster runs the same number of iterations (a tile index past the end is a dummy tile: TMA
-  // zero-fills its loads and drops its stores), which keeps the shared weight stream in lockstep.
-  const int unit0 = blockIdx.x / kCluster;
-  const int unit_step = gridDim.x / kCluster;
-  const int num_units = (args.num_tiles + kCluster - 1) / kCluster;
-  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCluster) - 1);
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&maps.w);
-    prefetch_tmap(&maps.pe);
-    for (int i = 0; i < kNL; ++i) prefetch_tmap(&maps.out[i]);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bar_wfull[i], 1);
-      mbar_init(&bar_wempty[i], kCluster);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_pefull[i], 1);
-      mbar_init(&bar_peempty[i], 1);
-      mbar_init(&bar_tfull[i], 1);
-    }
-    // one per output box: the 8 warps of a set
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&bar_st[i], 8);
-      mbar_init(&bar_stfree[i], kCopyWarps);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_holder);
-  if (warp >= 2 && warp < 18) {
-    const int t = threadIdx.x - 64;
-    for (int i = t; i < kNL * 256; i += kEpiThreads) {
-      const float* b = args.bias[i >> 8];
-      sBias[i] = b ? b[i & 255] : 0.f;
-    }
-    for (int i = t; i < 256; i += kEpiThreads) sHeadW[i] = args.head_w ? args.head_w[i] : 0.f;
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before anyone signals them
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_holder;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int ws = 0;
-      uint32_t wph = 0;
-      auto load_w = [&](int kcol) {
-        mbar_wait(&bar_wempty[ws], wph ^ 1);
-        if (kCluster == 1) {
-          mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
-          tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
-        } else {
-          mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
-          constexpr int kPart = kWBytes / kCluster;  // my share of the chunk: 256/kCluster features
-          tma_load_2d_mc(sW + ws * kWBytes + cta_rank * kPart, &maps.w, &bar_wfull[ws], kcol,
-                         cta_rank * (256 / kCluster), kMask);
-        }
-        if (++ws == kStages) {
-          ws = 0;
-          wph ^= 1;
-        }
-      };
-      auto load_pe = [&](int t, int tile) {
-        const int slot = t & 1;
-        mbar_wait(&bar_peempty[slot], ((t >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bar_pefull[slot], kBoxBytes);
-        tma_load_2d(sPE + slot * kBoxBytes, &maps.pe, &bar_pefull[slot], 0, tile * kTileM);
-      };
-      int t = 0;
-      if (unit0 < num_units) load_pe(0, unit0 * kCluster + cta_rank);
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        for (int l = 0; l < kNL; ++l) {
-          const LayerDesc& L = args.layer[l];
-          if (L.w_pe >= 0) load_w(L.w_pe);
-          if (l == 1) {  // the next tile's PE, one tile ahead
-            const int next = unit + unit_step;
-            if (next < num_units) load_pe(t + 1, next * kCluster + cta_rank);
-          }
-          if (L.w_act >= 0)
-            for (int b = 0; b < 4; ++b) load_w(L.w_act + b * 64);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    // The whole warp runs the loop (waits included) and ONE elected lane issues each tcgen05 op: with
-    // warp-uniform control flow the descriptor arithmetic stays in uniform registers.  A single
-    // diverged lane needed ~200 cycles of R2UR / ELECT / address math per MMA (ncu source view: 63 % of
-    // the issuing thread's samples in issue code, tensor pipe 35 % active) -- the issue thread, not
-    // the epilogue, paced the kernel.
-    {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
-      int ws = 0;
-      uint32_t wph = 0;
-      uint32_t act_ph = 0;
-      uint32_t g = 0;  // layers issued so far (accumulator = g & 1)
-      int t = 0;
-      auto free_stage = [&](uint64_t* bar) {
-        if (elect_one()) {
-          if (kCluster == 1) mma_commit(bar);
-          else mma_commit_mc(bar, kMask);  // the stage is refilled by BOTH producers of the cluster
-        }
-        __syncwarp();
-      };
-      auto commit_local = [&](uint64_t* bar) {
-        if (elect_one()) mma_commit(bar);
-        __syncwarp();
-      };
-      auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t& accum) {
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128);
-            const uint64_t db = umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128);
-            mma_bf16_ss(d, da, db, idesc, (k > 0) ? 1u : accum);
-          }
-        }
-        __syncwarp();
-        accum = 1;
-      };
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        const int slot = t & 1;
-        const uint32_t pe_ph = (t >> 1) & 1;
-        for (int l = 0; l < kNL; ++l, ++g) {
-          const LayerDesc& L = args.layer[l];
-          const uint32_t d_tmem = tmem_base + (g & 1) * 256;
-          uint32_t accum = 0;
-          if (L.w_pe >= 0) {
-            mbar_wait(&bar_pefull[slot], pe_ph);
-            mbar_wait(&bar_wfull[ws], wph);
-            tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32(sPE + slot * kBoxBytes);
-            const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-            mma4(d_tmem, a_addr, b_addr, accum);
-            free_stage(&bar_wempty[ws]);
-            if (L.pe_last) commit_local(&bar_peempty[slot]);
-            if (++ws == kStages) {
-              ws = 0;
-              wph ^= 1;
-            }
-          }
-          if (L.w_act >= 0) {
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-              mbar_wait(&bar_wfull[ws], wph);
-              mbar_wait(&bar_act[b], act_ph);
-              tc_fence_after_sync();
-              const uint32_t a_addr = smem_u32(sAct + b * kBoxBytes);
-              const uint32_t b_addr = smem_u32(sW + ws * kStageBytes);
-              mma4(d_tmem, a_addr, b_addr, accum);
-              free_stage(&bar_wempty[ws]);
-              if (++ws == kStages) {
-                ws = 0;
-                wph ^= 1;
-              }
-            }
-            act_ph ^= 1;
-          }
-          commit_local(&bar_tfull[g & 1]);
-        }
-      }
-    }
-  } else if (warp >= 18) {
-    // ------------------------------------------------------------ copy-out warps (lsu_store == 2)
-    // Each of the kCopyWarps warps owns 128 / kCopyWarps rows of every box: it waits for "box written",
-    // reads its rows out of the swizzled box (4 rows x 128 B per instruction, eight loads in flight)
-    // and streams them to HBM with coalesced 16-byte stores, then releases the box.  The epilogue warps
-    // neither store nor meet at a per-box barrier; they only check that the box they are about to
-    // overwrite was released (a whole layer earlier).
-    if (args.lsu_store == 2) {
-      const int cw = warp - 18;
-      constexpr int kRowsPer = kTileM / kCopyWarps;           // 64
-      const int r0 = cw * kRowsPer + (lane >> 3);              // my first row; rows r0 + 4 i
-      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
-      const uint32_t so_even = smem_u32(sAct) + r0 * 128 + x0, so_odd = smem_u32(sAct) + r0 * 128 + (x0 ^ 64u);
-      uint32_t ph = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
-        const int tile = unit * kCluster + cta_rank;
-        const int64_t rows_avail = args.M - static_cast<int64_t>(tile) * kTileM - r0;   // rows r0 + 4 i < M
-        for (int l = 0; l < kNL; ++l) {
-          if (!args.layer[l].store) continue;
-          const int64_t ldo = args.ld_out[l];
-          const bool fast = rows_avail >= kRowsPer;   // every row of mine exists
-          __nv_bfloat16* o0 = args.out[l] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
-#pragma unroll 1
-          for (int b = 0; b < 4; ++b) {
-            mbar_wait(&bar_st[b], ph);
-            copy_box_out<kRowsPer>(so_even + b * kBoxBytes, so_odd + b * kBoxBytes, o0 + b * 64, ldo, fast,
-                                   rows_avail, &bar_stfree[b], lane);
-          }
-          ph ^= 1;
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue warps
-    // Two sets of eight warps.  Set s owns the 64-column output boxes s and s+2 of every layer;
-    // inside a set, warp (quad, half) handles rows quad*32.. and the 32-column chunk `half` of
-    // the box, as two 16-column TMEM loads (the next load is in flight while one is processed).
-    // The epilogue is issue-bound, so everything per-chunk is kept off the per-element path:
-    // flags live in registers, shared memory is addressed explicitly, one mbarrier arrival per
-    // warp, one named barrier per box.
-    const int ew = warp - 2;
-    const int grp = ew >> 2;     // 0..3
-    const int half = grp & 1;    // which 32-column chunk of a box
-    const int set = grp >> 1;    // which boxes
-    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;
-    const bool lane0 = lane_id() == 0;
-    const bool leader = ((ew & 7) == 0) && lane0;  // one per set
-    const uint32_t set_bar = 2 + set;
-    const uint32_t sact_row = smem_u32(sAct) + row * 128;
-    const uint32_t sbias = smem_u32(sBias);
-    const uint32_t sheadw = smem_u32(sHeadW);
-    const uint32_t swz = row & 7;
-    // copy-out mapping (lsu_store): lane -> row cp_row0 + 4 i (i = 0..3) of the box, 16-byte chunk lane % 8.
-    // Row r keeps chunk c at position c ^ (r & 7); (r & 7) = lane / 8 for even i and lane / 8 + 4 for odd i.
-    const int cp_row0 = (ew & 7) * 16 + (lane >> 3);
-    const uint32_t cp_x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
-    const uint32_t cp_soff_even = cp_row0 * 128 + cp_x0;
-    const uint32_t cp_soff_odd = cp_row0 * 128 + (cp_x0 ^ 64u);
-    uint32_t g = 0;
-    uint32_t nst = 0;   // lsu_store == 2: stored layers so far (= releases seen per box)
-    const int st_mode = args.lsu_store;
-    for (int unit = unit0; unit < num_units; unit += unit_step) {
-      const int tile = unit * kCluster + cta_rank;
-      const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
-      const int64_t rows_left = args.M - static_cast<int64_t>(tile) * kTileM;   // rows of this tile that exist
-      for (int l = 0; l < kNL; ++l, ++g) {
-        const int relu = args.layer[l].relu, head = args.layer[l].head, feeds = args.layer[l].feeds;
-        const int store = args.layer[l].store;
-        // copy-out of this layer's boxes: where my lane's rows go (see cp_row0 above)
-        const int64_t out_ld = args.ld_out[l];
-        __nv_bfloat16* out_lane =
-            store ? args.out[l] + (static_cast<int64_t>(tile) * kTileM + cp_row0) * out_ld + (lane & 7) * 8 : nullptr;
-        mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
-        const bool want_mask = relu && args.relu_mask != nullptr;
-        uint32_t mbits = 0;
-        float hacc = 0.f;
-        uint32_t r[2][16];
-        tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int box = set + (q & 2);                  // q = 0,1: box s; q = 2,3: box s+2
-          const int col0 = box * 64 + half * 32 + (q & 1) * 16;
-          // copy-out warps: the previous contents of this box must have been read out before my first write
-          if (st_mode == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[box], (nst - 1) & 1);
-          // the bias of my 16 columns, requested before the wait for the accumulator chunk (its shared-memory
-          // latency was exposed in front of the first add: 8 % of the epilogue's samples)
-          float4 b4[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            b4[k] = lds128(sbias + (l * 256 + col0 + k * 4) * 4);
-          tmem_ld_wait_dep(r[q & 1]);
-          const uint32_t* rr = r[q & 1];
-          float v[16];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            v[k * 4 + 0] = __uint_as_float(rr[k * 4 + 0]) + b4[k].x;
-            v[k * 4 + 1] = __uint_as_float(rr[k * 4 + 1]) + b4[k].y;
-            v[k * 4 + 2] = __uint_as_float(rr[k * 4 + 2]) + b4[k].z;
-            v[k * 4 + 3] = __uint_as_float(rr[k * 4 + 3]) + b4[k].w;
-          }
-          if (q < 3) {
-            const int nbox = set + ((q + 1) & 2);
-            tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
-          }
-          if (relu) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (head) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 w4 = lds128(sheadw + (col0 + k * 4) * 4);
-              hacc += v[k * 4] * w4.x + v[k * 4 + 1] * w4.y + v[k * 4 + 2] * w4.z + v[k * 4 + 3] * w4.w;
-            }
-          }
-          uint4 o[2];
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          const uint32_t box_row = sact_row + box * kBoxBytes;
-          const uint32_t s0 = half * 4 + (q & 1) * 2;
-          sts128(box_row + ((s0 ^ swz) << 4), o[0]);
-          sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
-          if (want_mask) {
-            // ReLU mask: bit e = [column e of my 32-column chunk > 0].  v >= +0 after the ReLU, so its
-            // bit pattern is a non-negative integer and the sign of its negation is the predicate:
-            // one negate + one funnel shift per element
-            uint32_t m16 = 0;
-#pragma unroll
-            for (int i = 15; i >= 0; --i) {   // bit i of the group <- column e (relu_mask_bit order)
-              const int e = i >= 8 ? 2 * (i - 8) + 1 : 2 * i;
-              m16 = __funnelshift_l(static_cast<uint32_t>(-__float_as_int(v[e])), m16, 1);
-            }
-            mbits = (q & 1) ? (mbits | (m16 << 16)) : m16;
-          }
-          if (q & 1) {
-            // my 32-column chunk of the box is written
-            fence_proxy_async_smem();   // my writes -> visible to the async proxy (MMA, TMA store)
-            if (feeds) {
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_act[box]);   // one arrival per warp
-            }
-            // (after the hand-off: the proxy fence above is a full CTA membar and would otherwise wait
-            // for this global store's round trip before the MMA warp hears about the box)
-            if (want_mask)
-              args.relu_mask[((static_cast<int64_t>(tile) * 8 + l) * 8 + box * 2 + half) * kTileM + row] = mbits;
-            // Box complete once both halves are: store it.  The set's other box is written next;
-            // its previous store (the latest group of this leader) must have been read out.
-            if (store && st_mode == 2) {
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_st[box]);   // the copy-out warps take it from here
-            } else if (store && st_mode) {
-              named_bar_sync(set_bar, kSetThreads);   // the box is complete (both 32-column halves, all rows)
-              // my warp copies 16 of its 128 rows: lane -> (row = 4 i + lane / 8, 16-byte chunk = lane % 8)
-              // my warp copies 16 of the box's 128 rows, 4 rows x 128 B per instruction; all four loads
-              // are issued before the stores
-              const uint32_t sbox = smem_u32(sAct) + box * kBoxBytes;
-              float4 vv[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) vv[i] = lds128(sbox + ((i & 1) ? cp_soff_odd : cp_soff_even) + i * 512);
-              __nv_bfloat16* orow = out_lane + box * 64;
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (cp_row0 + i * 4 < rows_left) __stcs(reinterpret_cast<float4*>(orow + i * 4 * out_ld), vv[i]);
-            } else if (store) {
-              if (leader) tma_store_wait_read<0>();
-              named_bar_sync(set_bar, kSetThreads);
-              if (leader) {
-                tma_store_2d(&maps.out[l], sAct + box * kBoxBytes, box * 64, tile * kTileM);
-                tma_store_commit();
-              }
-            }
-          }
-        }
-        if (store) ++nst;
-        if (head) {
-          sHead[grp * kTileM + row] = hacc;
-          named_bar_sync(4, kEpiThreads);
-          if (grp == 0 && grow < args.M)
-            args.head_out[grow] = softplus_ref(sHead[row] + sHead[kTileM + row] + sHead[2 * kTileM + row] +
-                                               sHead[3 * kTileM + row] + args.head_b[0]);
-        }
-      }
-    }
-    if (leader) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still signal it
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-
 // =====================================================================================
-// Forward trunk, TWO tiles in flight per CTA ("ping-pong") -- the default forward kernel.
+// Forward trunk, two tiles in flight per CTA ("ping-pong").  kCluster = 2: the two CTAs of a cluster walk their
+// units in lockstep and share the weight stream -- each loads one half of every weight stage and TMA-multicasts it
+// into both CTAs, which halves the L2 reads (1.1 MB of weights per 128-sample tile).
 //
-// Why: with one tile per CTA the MMAs of layer l+1 cannot start before the epilogue of layer l has handed
+// Why two tiles: with one tile per CTA the MMAs of layer l+1 cannot start before the epilogue of layer l has handed
 // the activation boxes back, and the epilogue cannot start before the MMAs are complete.  A deletion
 // experiment (tools/trunk_variants.py: an epilogue that only waits, reads TMEM and arrives; copy-out warps that
 // only release) measured the bare MMA -> epilogue -> MMA round trip at ~3600 cycles per layer and tile against
@@ -963,27 +532,15 @@ mlp_trunk_fwd_pp_kernel(const __grid_constant__ TrunkMaps maps, const __grid_con
 //   dYl = (dY(l+1) . W(l+1)[:, h part]) * [Hl > 0],  l = 7..1      (j = 1..7)
 //
 // i.e. the autograd backward of models/nerf.py:84-93 with respect to the activations; the
-// weight gradients are separate launches that read the dY tensors this kernel stores.  Same
-// structure as the forward kernel: the gradient tile stays in shared memory between layers
-// (in place), weights (transposed) stream through 3 TMA stages shared by the CTA pair, the
-// accumulator is double buffered in TMEM.  The ReLU masks are the bit masks the forward kernel
-// wrote (32 B per sample and layer instead of re-reading 512 B of activations).  The incoming
-// dHF tile lands in its own 64 KB buffer, prefetched one tile ahead.
+// weight gradients are separate launches that read the dY tensors this kernel stores.  The ReLU
+// masks are the bit masks the forward kernel wrote (32 B per sample and layer instead of re-reading
+// 512 B of activations).
 namespace bwd {
 
 constexpr int kNLb = UPNERF_TRUNK_BWD_LAYERS;  // 8
-constexpr int kOffIn = 0;
-constexpr int kOffActB = kOffIn + kActBytes;
-constexpr int kOffWB = kOffActB + kActBytes;
-constexpr int kOffSigW = kOffWB + kWStages * kWBytes;
-constexpr int kOffBarB = kOffSigW + 256 * 4;
-constexpr int kNumBarsB = 2 * kWStages + 2 + 4 + 2 + 8;
-constexpr int kOffTmemB = kOffBarB + kNumBarsB * 8;
-constexpr int kSmemBytesB = kOffTmemB + 16 + 1024;
-static_assert(kSmemBytesB <= 232448, "shared memory budget exceeded");
 
 struct BwdMaps {
-  CUtensorMap w, in, out[kNLb];
+  CUtensorMap w, in;
 };
 struct BwdArgs {
   int64_t M;
@@ -991,300 +548,9 @@ struct BwdArgs {
   const float* d_ssig;
   const float* sig_w;
   const uint32_t* relu_mask;
-  int lsu_store;                 // see TrunkArgs::lsu_store
   __nv_bfloat16* out[UPNERF_TRUNK_BWD_LAYERS];
   int64_t ld_out[UPNERF_TRUNK_BWD_LAYERS];
 };
-
-template <int kCluster>
-__global__ void __launch_bounds__(kThreadsF, 1)
-mlp_trunk_bwd_kernel(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdArgs args) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint8_t* sIn = smem + kOffIn;
-  uint8_t* sAct = smem + kOffActB;
-  uint8_t* sW = smem + kOffWB;
-  float* sSigW = reinterpret_cast<float*>(smem + kOffSigW);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarB);
-  uint64_t* bar_wfull = bars;
-  uint64_t* bar_wempty = bars + kWStages;
-  uint64_t* bar_infull = bars + 2 * kWStages;
-  uint64_t* bar_inempty = bars + 2 * kWStages + 1;
-  uint64_t* bar_act = bars + 2 * kWStages + 2;
-  uint64_t* bar_tfull = bars + 2 * kWStages + 6;
-  uint64_t* bar_st = bar_tfull + 2;        // [4] lsu_store == 2: box written -> copy-out warps (see forward)
-  uint64_t* bar_stfree = bar_st + 4;       // [4] box copied out -> may be overwritten
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + kOffTmemB);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int cta_rank = kCluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int unit0 = blockIdx.x / kCluster;
-  const int unit_step = gridDim.x / kCluster;
-  const int num_units = (args.num_tiles + kCluster - 1) / kCluster;
-  constexpr uint16_t kMask = static_cast<uint16_t>((1u << kCluster) - 1);
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&maps.w);
-    prefetch_tmap(&maps.in);
-    for (int i = 0; i < kNLb; ++i) prefetch_tmap(&maps.out[i]);
-    for (int i = 0; i < kWStages; ++i) {
-      mbar_init(&bar_wfull[i], 1);
-      mbar_init(&bar_wempty[i], kCluster);
-    }
-    mbar_init(bar_infull, 1);
-    mbar_init(bar_inempty, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&bar_tfull[i], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&bar_act[i], 8);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&bar_st[i], 8);
-      mbar_init(&bar_stfree[i], kCopyWarps);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_holder);
-  if (warp >= 2 && warp < 18)
-    for (int i = threadIdx.x - 64; i < 256; i += kEpiThreads) sSigW[i] = args.sig_w ? args.sig_w[i] : 0.f;
-  tc_fence_before_sync();
-  __syncthreads();
-  if (kCluster > 1) cluster_sync_all();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_holder;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int ws = 0;
-      uint32_t wph = 0;
-      auto load_w = [&](int kcol) {
-        mbar_wait(&bar_wempty[ws], wph ^ 1);
-        mbar_arrive_expect_tx(&bar_wfull[ws], kWBytes);
-        if (kCluster == 1) {
-          tma_load_2d(sW + ws * kWBytes, &maps.w, &bar_wfull[ws], kcol, 0);
-        } else {
-          constexpr int kPart = kWBytes / kCluster;
-          tma_load_2d_mc(sW + ws * kWBytes + cta_rank * kPart, &maps.w, &bar_wfull[ws], kcol,
-                         cta_rank * (256 / kCluster), kMask);
-        }
-        if (++ws == kWStages) {
-          ws = 0;
-          wph ^= 1;
-        }
-      };
-      auto load_in = [&](int t, int tile) {
-        mbar_wait(bar_inempty, (t & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_infull, kActBytes);
-        for (int b = 0; b < 4; ++b)
-          tma_load_2d(sIn + b * kBoxBytes, &maps.in, bar_infull, b * 64, tile * kTileM);
-      };
-      int t = 0;
-      if (unit0 < num_units) load_in(0, unit0 * kCluster + cta_rank);
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        for (int j = 0; j < kNLb; ++j) {
-          for (int b = 0; b < 4; ++b) load_w(j * 256 + b * 64);
-          if (j == 1) {  // layer 0's MMAs have retired by now: its input buffer is free
-            const int next = unit + unit_step;
-            if (next < num_units) load_in(t + 1, next * kCluster + cta_rank);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    // warp-uniform loop, one elected lane issues (see the forward kernel)
-    {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, 256, 0, 0);
-      int ws = 0;
-      uint32_t wph = 0;
-      uint32_t act_ph = 0;
-      uint32_t g = 0;
-      int t = 0;
-      auto free_stage = [&](uint64_t* bar) {
-        if (elect_one()) {
-          if (kCluster == 1) mma_commit(bar);
-          else mma_commit_mc(bar, kMask);
-        }
-        __syncwarp();
-      };
-      auto commit_local = [&](uint64_t* bar) {
-        if (elect_one()) mma_commit(bar);
-        __syncwarp();
-      };
-      for (int unit = unit0; unit < num_units; unit += unit_step, ++t) {
-        for (int j = 0; j < kNLb; ++j, ++g) {
-          const uint32_t d_tmem = tmem_base + (g & 1) * 256;
-          uint32_t accum = 0;
-          if (j == 0) mbar_wait(bar_infull, t & 1);
-#pragma unroll 1
-          for (int b = 0; b < 4; ++b) {
-            mbar_wait(&bar_wfull[ws], wph);
-            if (j > 0) mbar_wait(&bar_act[b], act_ph);
-            tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32((j == 0 ? sIn : sAct) + b * kBoxBytes);
-            const uint32_t b_addr = smem_u32(sW + ws * kWBytes);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma_bf16_ss(d_tmem, umma_desc(a_addr + k * 32, 16, 1024, kLayoutSw128),
-                            umma_desc(b_addr + k * 32, 16, 1024, kLayoutSw128), idesc, (k > 0) ? 1u : accum);
-            }
-            __syncwarp();
-            accum = 1;
-            free_stage(&bar_wempty[ws]);
-            if (++ws == kWStages) {
-              ws = 0;
-              wph ^= 1;
-            }
-          }
-          if (j == 0) commit_local(bar_inempty);
-          else act_ph ^= 1;
-          commit_local(&bar_tfull[g & 1]);
-        }
-      }
-    }
-  } else if (warp >= 18) {
-    // ------------------------------------------------------------ copy-out warps (lsu_store == 2, see forward)
-    if (args.lsu_store == 2) {
-      const int cw = warp - 18;
-      constexpr int kRowsPer = kTileM / kCopyWarps;
-      const int r0 = cw * kRowsPer + (lane >> 3);
-      const uint32_t x0 = static_cast<uint32_t>((lane & 7) ^ (lane >> 3)) << 4;
-      const uint32_t so_even = smem_u32(sAct) + r0 * 128 + x0, so_odd = smem_u32(sAct) + r0 * 128 + (x0 ^ 64u);
-      uint32_t ph = 0;
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
-        const int tile = unit * kCluster + cta_rank;
-        const int64_t rows_avail = args.M - static_cast<int64_t>(tile) * kTileM - r0;
-        for (int j = 0; j < kNLb; ++j) {
-          const int64_t ldo = args.ld_out[j];
-          const bool fast = rows_avail >= kRowsPer;   // every row of mine exists
-          __nv_bfloat16* o0 = args.out[j] + (static_cast<int64_t>(tile) * kTileM + r0) * ldo + (lane & 7) * 8;
-#pragma unroll 1
-          for (int bx = 0; bx < 4; ++bx) {
-            mbar_wait(&bar_st[bx], ph);
-            copy_box_out<kRowsPer>(so_even + bx * kBoxBytes, so_odd + bx * kBoxBytes, o0 + bx * 64, ldo, fast,
-                                   rows_avail, &bar_stfree[bx], lane);
-          }
-          ph ^= 1;
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue warps (see forward)
-    const int ew = warp - 2;
-    const int grp = ew >> 2;
-    const int half = grp & 1;
-    const int set = grp >> 1;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const bool lane0 = lane_id() == 0;
-    const bool leader = ((ew & 7) == 0) && lane0;
-    const uint32_t set_bar = 2 + set;
-    const uint32_t sact_row = smem_u32(sAct) + row * 128;
-    const uint32_t ssigw = smem_u32(sSigW);
-    const uint32_t swz = row & 7;
-    uint32_t g = 0;
-    uint32_t nst = 0;   // lsu_store == 2: layers stored so far (= releases seen per box)
-    const int st_mode = args.lsu_store;
-    for (int unit = unit0; unit < num_units; unit += unit_step) {
-      const int tile = unit * kCluster + cta_rank;
-      const int64_t grow = static_cast<int64_t>(tile) * kTileM + row;
-      const bool in_range = tile < args.num_tiles;
-      const float ds = (args.d_ssig && grow < args.M) ? args.d_ssig[grow] : 0.f;
-      for (int j = 0; j < kNLb; ++j, ++g) {
-        // ReLU mask words of H(8-j) for my two chunks (forward layer index 7-j); issued before the
-        // accumulator wait so the loads are long done when they are needed
-        const uint32_t* mrow =
-            args.relu_mask + ((static_cast<int64_t>(in_range ? tile : 0) * 8 + (7 - j)) * 8) * kTileM + row;
-        const uint32_t mA = __ldg(mrow + (set * 2 + half) * kTileM);
-        const uint32_t mB = __ldg(mrow + ((set + 2) * 2 + half) * kTileM);
-        mbar_wait(&bar_tfull[g & 1], (g >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (g & 1) * 256;
-        uint32_t r[2][16];
-        tmem_ld_32x16(taddr + (2 * set + half) * 32, r[0]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int box = set + (q & 2);
-          const int col0 = box * 64 + half * 32 + (q & 1) * 16;
-          if (st_mode == 2 && (q & 1) == 0 && nst) mbar_wait(&bar_stfree[box], (nst - 1) & 1);
-          tmem_ld_wait_dep(r[q & 1]);
-          if (q < 3) {
-            const int nbox = set + ((q + 1) & 2);
-            tmem_ld_32x16(taddr + nbox * 64 + half * 32 + ((q + 1) & 1) * 16, r[(q + 1) & 1]);
-          }
-          const uint32_t* rr = r[q & 1];
-          const uint32_t m16 = ((q & 2) ? mB : mA) >> ((q & 1) * 16);
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(rr[e]);
-          if (j == 0) {
-            // + d_ssig (x) w_sigma : the share_sigma head hangs off H8 (models/nerf.py:89)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float4 w4 = lds128(ssigw + (col0 + k * 4) * 4);
-              v[k * 4 + 0] += ds * w4.x;
-              v[k * 4 + 1] += ds * w4.y;
-              v[k * 4 + 2] += ds * w4.z;
-              v[k * 4 + 3] += ds * w4.w;
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = ((m16 >> relu_mask_bit(e)) & 1u) ? v[e] : 0.f;
-          uint4 o[2];
-          __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) ob[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          const uint32_t box_row = sact_row + box * kBoxBytes;
-          const uint32_t s0 = half * 4 + (q & 1) * 2;
-          sts128(box_row + ((s0 ^ swz) << 4), o[0]);
-          sts128(box_row + (((s0 + 1) ^ swz) << 4), o[1]);
-          if (q & 1) {
-            fence_proxy_async_smem();
-            if (j < kNLb - 1) {
-              tc_fence_before_sync();
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_act[box]);
-            }
-            if (st_mode == 2) {
-              __syncwarp();
-              if (lane0) mbar_arrive(&bar_st[box]);
-            } else if (st_mode) {
-              named_bar_sync(set_bar, kSetThreads);
-              const int w8 = ew & 7;
-              __nv_bfloat16* obase = args.out[j] + box * 64 + (lane & 7) * 8;
-              const uint32_t sbox = smem_u32(sAct) + box * kBoxBytes;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int rr2 = w8 * 16 + i * 4 + (lane >> 3);
-                const float4 vv = lds128(sbox + rr2 * 128 + ((((lane & 7) ^ (rr2 & 7))) << 4));
-                const int64_t gr = static_cast<int64_t>(tile) * kTileM + rr2;
-                if (gr < args.M) __stcs(reinterpret_cast<float4*>(obase + gr * args.ld_out[j]), vv);
-              }
-            } else {
-              if (leader) tma_store_wait_read<0>();
-              named_bar_sync(set_bar, kSetThreads);
-              if (leader) {
-                tma_store_2d(&maps.out[j], sAct + box * kBoxBytes, box * 64, tile * kTileM);
-                tma_store_commit();
-              }
-            }
-          }
-        }
-        ++nst;
-      }
-    }
-    if (leader) tma_store_wait_all<0>();
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (kCluster > 1) cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
 
 }  // namespace bwd
 
@@ -1597,6 +863,36 @@ int trunk_cluster_size() {
 }  // namespace
 }  // namespace upnerf
 
+// Launch of either trunk kernel: one cluster of `cluster` CTAs per unit of 2 * cluster tiles, at most one CTA per SM
+template <typename K1, typename K2, typename Maps, typename Args>
+static int launch_trunk(K1 k1, K2 k2, int cluster, int64_t tiles, int smem_bytes, cudaStream_t st, const Maps& maps,
+                        const Args& args) {
+  using namespace upnerf;
+  const int64_t units = ceil_div64(tiles, 2 * cluster);
+  if (cluster == 1) {
+    const int grid = static_cast<int>(units < sm_count() ? units : sm_count());
+    k1<<<grid, kThreadsF, smem_bytes, st>>>(maps, args);
+    return UPNERF_OK;
+  }
+  const int max_clusters = sm_count() / 2;
+  const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreadsF);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2, maps, args));
+  return UPNERF_OK;
+}
+
 extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* stream) {
   using namespace upnerf;
   UPNERF_REQUIRE(a && a->M > 0, UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: M=%lld", a ? (long long)a->M : -1ll);
@@ -1613,55 +909,34 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
   args.M = a->M;
   args.num_tiles = static_cast<int>(tiles);
   const int cluster = trunk_cluster_size();
-  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat, 256, UPNERF_TRUNK_WCAT_COLS, a->ld_w, 256 / cluster, 64));
+  // a weight stage is one N-half of a K-chunk: 128 / cluster output features per TMA box (multicast across the pair)
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat, 256, UPNERF_TRUNK_WCAT_COLS, a->ld_w, 128 / cluster, 64));
   UPNERF_TRY(make_tmap_bf16_2d(&maps.pe, a->pe, a->M, 64, a->ld_pe, kTileM, 64));
   // Wcat columns: [W1 (64) | W2 | W3 | W4 | W5 = [h (256) | PE (64)] | W6 | W7 | W8 | WF]
   const int w_act[kNL] = {-1, 64, 320, 576, 832, 1152, 1408, 1664, 1920};
   const int w_pe[kNL] = {0, -1, -1, -1, 1088, -1, -1, -1, -1};
+  int n_store = 0;
   for (int l = 0; l < kNL; ++l) {
     LayerDesc& L = args.layer[l];
     L.store = a->out[l] != nullptr;
-    if (L.store) UPNERF_TRY(make_tmap_bf16_2d(&maps.out[l], a->out[l], a->M, 256, a->ld_out[l], kTileM, 64));
-    else maps.out[l] = maps.pe;  // never used
+    n_store += L.store;
     L.w_act = w_act[l];
     L.w_pe = w_pe[l];
-    L.relu = l < 8;
-    L.feeds = l < 8;
-    L.head = l == 7;
+    // (the epilogue's layer kinds are compile-time: Linear + ReLU for l = 0..6, + share_sigma head for l = 7, linear l = 8)
     L.pe_last = l == 4;
     args.bias[l] = a->bias[l];
+    args.out[l] = static_cast<__nv_bfloat16*>(a->out[l]);
+    args.ld_out[l] = a->ld_out[l];
+    // the copy-out warps store 16-byte vectors: every row must start 16-byte aligned
+    UPNERF_REQUIRE(!a->out[l] || ((reinterpret_cast<uintptr_t>(a->out[l]) & 15) == 0 && (a->ld_out[l] & 7) == 0),
+                   UPNERF_ERR_BAD_SHAPE, "mlp_trunk_fwd: out[%d] must be 16-byte aligned with ld %% 8 == 0", l);
   }
   args.head_w = a->sigma_w;
   args.head_b = a->sigma_b;
   args.head_out = a->s_sigma;
   args.relu_mask = a->relu_mask;
-  {
-    // 0: TMA stores; 1: the epilogue warps copy their set's box out; 2: two dedicated copy-out warps
-    const char* e = getenv("UPNERF_TRUNK_LSU_STORE");
-    args.lsu_store = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
-    for (int l = 0; l < kNL; ++l) {
-      args.out[l] = static_cast<__nv_bfloat16*>(a->out[l]);
-      args.ld_out[l] = a->ld_out[l];
-      // 16-byte vector stores need 8-element alignment of every row
-      if (a->out[l] && ((reinterpret_cast<uintptr_t>(a->out[l]) & 15) != 0 || (a->ld_out[l] & 7) != 0))
-        args.lsu_store = 0;
-    }
-  }
-  // default: two tiles in flight per CTA (pp::mlp_trunk_fwd_pp_kernel); UPNERF_TRUNK_PP=0 or a store path other
-  // than the copy-out warps selects the single-tile kernel
-  bool use_pp = args.lsu_store == 2;
-  {
-    const char* e = getenv("UPNERF_TRUNK_PP");
-    if (e && e[0] == '0') use_pp = false;
-  }
-  if (use_pp)   // the ping-pong kernel stages N-halves of a weight chunk: 128 / cluster output features per box
-    UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat, 256, UPNERF_TRUNK_WCAT_COLS, a->ld_w, 128 / cluster, 64));
   static bool attr_set = false;
   if (!attr_set) {
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytes));
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytes));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(pp::mlp_trunk_fwd_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            pp::kSmemBytesP));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(pp::mlp_trunk_fwd_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1669,39 +944,12 @@ extern "C" int upnerf_mlp_trunk_fwd_bf16(const upnerf_trunk_args* a, void* strea
     attr_set = true;
   }
   const double flop = 2.0 * a->M * 256.0 * (64 + 7 * 256 + 320);
-  // algorithmic traffic: read PE, write nine activation tensors + the ReLU bit masks
-  int n_store = 0;
-  for (int l = 0; l < kNL; ++l) n_store += args.layer[l].store;
+  // algorithmic traffic: read PE, write the stored activation tensors + the ReLU bit masks
   const double bytes = 2.0 * a->M * (64 + n_store * 256) + (a->relu_mask ? 8.0 * 32 * a->M : 0.0);
   LaunchScope scope(kCatTrunkFwd, as_stream(stream), flop, bytes);
-  const int tiles_per_unit = use_pp ? 2 : 1;
-  const int smem_bytes = use_pp ? pp::kSmemBytesP : kSmemBytes;
-  if (cluster == 1) {
-    const int64_t units = ceil_div64(tiles, tiles_per_unit);
-    const int grid = static_cast<int>(units < sm_count() ? units : sm_count());
-    if (use_pp) pp::mlp_trunk_fwd_pp_kernel<1><<<grid, kThreadsF, smem_bytes, as_stream(stream)>>>(maps, args);
-    else mlp_trunk_fwd_kernel<1><<<grid, kThreadsF, smem_bytes, as_stream(stream)>>>(maps, args);
-  } else {
-    const int64_t units = ceil_div64(tiles, 2 * tiles_per_unit);
-    const int max_clusters = sm_count() / 2;
-    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreadsF);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (use_pp) UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pp::mlp_trunk_fwd_pp_kernel<2>, maps, args));
-    else UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_fwd_kernel<2>, maps, args));
-  }
-  UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_kernel");
+  UPNERF_TRY(launch_trunk(pp::mlp_trunk_fwd_pp_kernel<1>, pp::mlp_trunk_fwd_pp_kernel<2>, cluster, tiles,
+                          pp::kSmemBytesP, as_stream(stream), maps, args));
+  UPNERF_CHECK_LAUNCH("mlp_trunk_fwd_pp_kernel");
   return UPNERF_OK;
 }
 
@@ -1731,35 +979,17 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
   args.sig_w = a->sigma_w;
   args.relu_mask = a->relu_mask;
   const int cluster = trunk_cluster_size();
-  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 256 / cluster, 64));
+  UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 128 / cluster, 64));
   UPNERF_TRY(make_tmap_bf16_2d(&maps.in, a->d_hf, a->M, 256, a->ld_dhf, kTileM, 64));
-  {
-    // Backward: the epilogue-copy variant (1) is faster alone (1.11 -> 1.03 ms at M = 786k) but not inside
-    // the train step (1.10 -> 1.15 ms next to the side stream's HBM-heavy leaves); the copy-out warps (2)
-    // gain there as well (1.18 -> 1.05 ms).
-    const char* e = getenv("UPNERF_TRUNK_BWD_STORE");     // 0: TMA stores, 1: epilogue copy, 2: copy-out warps (default)
-    args.lsu_store = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
-  }
   for (int j = 0; j < kNLb; ++j) {
     UPNERF_REQUIRE(a->d_out[j], UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: d_out[%d] missing", j);
-    UPNERF_TRY(make_tmap_bf16_2d(&maps.out[j], a->d_out[j], a->M, 256, a->ld_dout[j], kTileM, 64));
+    UPNERF_REQUIRE((reinterpret_cast<uintptr_t>(a->d_out[j]) & 15) == 0 && (a->ld_dout[j] & 7) == 0,
+                   UPNERF_ERR_BAD_SHAPE, "mlp_trunk_bwd: d_out[%d] must be 16-byte aligned with ld %% 8 == 0", j);
     args.out[j] = static_cast<__nv_bfloat16*>(a->d_out[j]);
     args.ld_out[j] = a->ld_dout[j];
-    if ((reinterpret_cast<uintptr_t>(a->d_out[j]) & 15) != 0 || (a->ld_dout[j] & 7) != 0) args.lsu_store = 0;
   }
-  bool use_pp = args.lsu_store == 2;
-  {
-    const char* e = getenv("UPNERF_TRUNK_PP");
-    if (e && e[0] == '0') use_pp = false;
-  }
-  if (use_pp)
-    UPNERF_TRY(make_tmap_bf16_2d(&maps.w, a->wcat_t, 256, UPNERF_TRUNK_WCATT_COLS, a->ld_w, 128 / cluster, 64));
   static bool attr_set = false;
   if (!attr_set) {
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytesB));
-    UPNERF_CHECK_CUDA(cudaFuncSetAttribute(mlp_trunk_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytesB));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(pp::mlp_trunk_bwd_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            pp::kSmemBytesBP));
     UPNERF_CHECK_CUDA(cudaFuncSetAttribute(pp::mlp_trunk_bwd_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1770,33 +1000,8 @@ extern "C" int upnerf_mlp_trunk_bwd_bf16(const upnerf_trunk_bwd_args* a, void* s
   // algorithmic traffic: read dHF + bit masks + d_ssig, write eight gradient tensors
   const double bytes = 2.0 * a->M * (256 + 8 * 256) + 8.0 * 32 * a->M + 4.0 * a->M;
   LaunchScope scope(kCatTrunkBwd, as_stream(stream), flop, bytes);
-  const int tiles_per_unit = use_pp ? 2 : 1;
-  const int smem_bytes = use_pp ? pp::kSmemBytesBP : kSmemBytesB;
-  if (cluster == 1) {
-    const int64_t units = ceil_div64(tiles, tiles_per_unit);
-    const int grid = static_cast<int>(units < sm_count() ? units : sm_count());
-    if (use_pp) pp::mlp_trunk_bwd_pp_kernel<1><<<grid, kThreadsF, smem_bytes, as_stream(stream)>>>(maps, args);
-    else mlp_trunk_bwd_kernel<1><<<grid, kThreadsF, smem_bytes, as_stream(stream)>>>(maps, args);
-  } else {
-    const int64_t units = ceil_div64(tiles, 2 * tiles_per_unit);
-    const int max_clusters = sm_count() / 2;
-    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreadsF);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (use_pp) UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pp::mlp_trunk_bwd_pp_kernel<2>, maps, args));
-    else UPNERF_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mlp_trunk_bwd_kernel<2>, maps, args));
-  }
-  UPNERF_CHECK_LAUNCH("mlp_trunk_bwd_kernel");
+  UPNERF_TRY(launch_trunk(pp::mlp_trunk_bwd_pp_kernel<1>, pp::mlp_trunk_bwd_pp_kernel<2>, cluster, tiles,
+                          pp::kSmemBytesBP, as_stream(stream), maps, args));
+  UPNERF_CHECK_LAUNCH("mlp_trunk_bwd_pp_kernel");
   return UPNERF_OK;
 }
