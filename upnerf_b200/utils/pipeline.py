@@ -14,7 +14,12 @@ import torch
 
 
 class DevicePrefetcher:
-    """Iterate device batches from an iterable of dicts of pinned host tensors, one batch ahead."""
+    """Iterate device batches from an iterable of dicts of pinned host tensors, one batch ahead.
+
+    The device side is TWO preallocated sets of tensors filled alternately on a copy stream (no allocation,
+    no `record_stream` bookkeeping per step): the copy into a set waits -- on the copy stream, never on the
+    host -- for the event that marks the end of the compute-stream work that was queued when the set was last
+    handed out.  A yielded batch stays valid until the batch after the next one is requested."""
 
     def __init__(self, batches, device):
         self.it = iter(batches)
@@ -22,6 +27,9 @@ class DevicePrefetcher:
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher: CUDA device required")
         self.stream = torch.cuda.Stream(device=self.device)
+        self._bufs = [None, None]
+        self._free = [None, None]      # compute-stream event after which set i may be overwritten
+        self._n = 0
         self._next = None
         self._stage()
 
@@ -31,11 +39,21 @@ class DevicePrefetcher:
         except StopIteration:
             self._next = None
             return
+        i = self._n & 1
+        self._n += 1
+        bufs = self._bufs[i]
+        if bufs is None or any(k not in bufs or bufs[k].shape != v.shape or bufs[k].dtype != v.dtype
+                               for k, v in host.items()):
+            bufs = self._bufs[i] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))   # (allocated on the compute stream)
         with torch.cuda.stream(self.stream):
-            dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
+            if self._free[i] is not None:
+                self.stream.wait_event(self._free[i])
+            for k, v in host.items():
+                bufs[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self._next = (dev, ev)
+        self._next = (i, ev)
 
     def __iter__(self):
         return self
@@ -43,36 +61,53 @@ class DevicePrefetcher:
     def __next__(self):
         if self._next is None:
             raise StopIteration
-        dev, ev = self._next
+        i, ev = self._next
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
-        for v in dev.values():
-            v.record_stream(cur)        # allocated on the copy stream, consumed on the compute stream
+        # everything queued on the compute stream so far (the step that consumed the other set included) precedes
+        # this event: once it has fired the other set may be refilled
+        fe = torch.cuda.Event()
+        fe.record(cur)
+        self._free[i ^ 1] = fe
+        dev = self._bufs[i]
         self._stage()                   # batch i+1 starts copying before step i is issued
         return dev
 
 
 class DelayedScalar:
-    """`push(t)` enqueues the D2H copy of a device scalar and returns the value pushed one call
-    earlier (None the first time); `last()` drains the final one."""
+    """`push(t)` enqueues the D2H copy of a device scalar and returns the value pushed `depth` calls earlier (None
+    until then); `drain()` returns the values still in flight, oldest first (`last()`: the newest one).  Every
+    pushed scalar is read on the host exactly once; with depth > 1 the host may run that many steps ahead of the
+    device, which rides out a descheduled host thread without idling the GPU."""
 
-    def __init__(self):
-        self.slots = [torch.empty((), pin_memory=True), torch.empty((), pin_memory=True)]
-        self.events = [None, None]
+    def __init__(self, depth: int = 1):
+        self.depth = max(1, int(depth))
+        self.slots = [torch.empty((), pin_memory=True) for _ in range(self.depth + 1)]
+        self.events = [None] * (self.depth + 1)
         self.n = 0
+        self.read = 0
 
     def push(self, t: torch.Tensor):
-        i = self.n & 1
+        i = self.n % (self.depth + 1)
         self.slots[i].copy_(t.detach().reshape(()), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         self.events[i] = ev
         self.n += 1
-        return self._read(i ^ 1) if self.n > 1 else None
+        return self._read_next() if self.n - self.read > self.depth else None
 
-    def _read(self, i):
+    def _read_next(self):
+        i = self.read % (self.depth + 1)
         self.events[i].synchronize()
+        self.read += 1
         return float(self.slots[i])
 
+    def drain(self):
+        out = []
+        while self.read < self.n:
+            out.append(self._read_next())
+        return out
+
     def last(self):
-        return self._read((self.n - 1) & 1) if self.n else None
+        vals = self.drain()
+        return vals[-1] if vals else None
