@@ -399,6 +399,12 @@ typedef struct upnerf_render_args {
   uint64_t workspace_bytes;
   int no_grad;               /* 1: forward only (inference): activations are not kept, the
                                 workspace is ~4x smaller and upnerf_render_bwd is refused */
+  int reuse_packed;          /* no_grad only.  1: the packed GEMM operands, folded head matrices and c2f band
+                                weights a previous upnerf_render_fwd call left in THIS workspace (same
+                                pointer, same sizes and configuration) are still valid -- parameters and
+                                `progress` have not changed -- and are not rebuilt.  The chunk loop of a
+                                full-image render (reference models/nerf_system.py:104-126) sets it for
+                                every chunk after the first. */
 } upnerf_render_args;
 
 int64_t upnerf_nerf_param_count(const upnerf_net_config* cfg);

@@ -124,6 +124,11 @@ def test_graphed_inference_chunks_equal_eager(cuda_dev, precision):
     with torch.no_grad():                      # parameters move: the replays must see the new values
         sys_.nerf_fine.rgb_share_layer[2].bias.add_(0.25)
         sys_.embedding_fine_a.weight.mul_(1.5)
+        # ... including the operands that only the FIRST chunk of a render packs (the other chunks reuse them)
+        sys_.nerf_fine.xyz_encoding_2[0].weight.mul_(1.05)
+        sys_.nerf_coarse.xyz_encoding_final.weight.mul_(0.97)
+        sys_.nerf_fine.rgb_share_layer[0].weight.mul_(1.02)
+    sys_.set_progress(0.6)
     ref2, got2 = render(False), render(True)
     assert not torch.equal(ref2["rgb_fine"], ref["rgb_fine"])
     for k in ref2:

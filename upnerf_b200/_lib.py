@@ -220,7 +220,8 @@ class RenderArgs(C.Structure):
                 ("rays", C.c_void_p), ("img_idx", C.c_void_p), ("perturb_rand", C.c_void_p),
                 ("u0", C.c_void_p), ("u1", C.c_void_p), ("coarse", PassIO), ("fine", PassIO),
                 ("z_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("d_rays", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("no_grad", C.c_int)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("no_grad", C.c_int),
+                ("reuse_packed", C.c_int)]
 
 
 _TAIL_IN = ("img_idx", "inv_depths", "depth_scale", "rgbs", "feats", "s_depth_c", "s_depth_f", "t_weight_c",

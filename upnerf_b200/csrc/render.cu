@@ -442,7 +442,8 @@ upnerf_epilogue ep_none() {
 // operands -- behind the folded-matrix product Wq = W_rgb0[:, :F] W_sf -- on the side stream `cl`,
 // which the caller joins before the first head layer.
 int pack_weights(const Ctx& c, const Ctx& cl, const upnerf_net_config& cfg, const NetLayout& L, const Phase& ph,
-                 const float* prm, Packed& k) {
+                 const float* prm, Packed& k, bool reuse) {
+  if (reuse) return fork_side(c);   // inference chunk after the first: everything below is still in the workspace
   UPNERF_CHECK_CUDA(cudaMemsetAsync(k.region, 0, k.region_bytes, c.st));
   UPNERF_TRY(upnerf_c2f_weights(prm + L.progress, cfg.c2f_start, cfg.c2f_end, cfg.use_c2f, cfg.xyz_L,
                                 k.band_xyz, c.st));
@@ -512,7 +513,8 @@ int pass_prologue(const Ctx& c, const upnerf_render_args& a, const NetLayout& L,
   const int64_t R = p.R;
   Packed& k = p.pk;
   const Ctx cl = c.leaf();
-  UPNERF_TRY(pack_weights(c, cl, cfg, L, ph, prm, k));   // forks the side stream
+  const bool reuse = a.no_grad && a.reuse_packed;
+  UPNERF_TRY(pack_weights(c, cl, cfg, L, ph, prm, k, reuse));   // forks the side stream
 
   // Per-ray inputs of the head layers (embeddings, direction encoding) enter as a per-ray bias
   // W[:, cols] e_ray: computed on the side stream while the trunk runs.
@@ -542,7 +544,7 @@ int pass_prologue(const Ctx& c, const upnerf_render_args& a, const NetLayout& L,
     e.bias = k.bq_const;
     UPNERF_TRY(mm(cl, p.P, pw, 1, prm + L.Wr0 + front, L.rgb_in, 1, Bq, ldbias, 1, R, H, pw, &e, 0));
   }
-  if (stack) {
+  if (stack && !reuse) {
     // rgb_share_layer.2 row-dots see only the Q half of the stacked output
     UPNERF_CHECK_CUDA(cudaMemsetAsync(k.hw3, 0, 3 * H2 * sizeof(float), cl.st));
     UPNERF_CHECK_CUDA(cudaMemcpy2DAsync(k.hw3 + H, H2 * sizeof(float), prm + L.Wr2, H * sizeof(float),

@@ -118,7 +118,17 @@ class _RenderFn(torch.autograd.Function):
             meta["depths"].update(z_coarse=zc, z_fine=zf)
         a.workspace_bytes = 0
         nbytes = L.render_workspace_bytes(a)
-        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        # inference chunk loops pass `workspace_cache` (a dict): every chunk then runs in the SAME workspace, which
+        # lets the chunks after the first skip the parameter-only prologue (`reuse_packed`)
+        wsc = meta.get("workspace_cache")
+        ws = None if wsc is None else wsc.get(nbytes)
+        a.reuse_packed = 0
+        if ws is None or ws.device != dev:
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            if wsc is not None:
+                wsc[nbytes] = ws
+        elif meta.get("reuse_packed") and a.no_grad:
+            a.reuse_packed = 1
         a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
         L.render_fwd(a)
         ctx.args, ctx.keep, ctx.ws, ctx.names, ctx.meta = a, keep, ws, names, meta
@@ -229,7 +239,8 @@ def render_rays(models, embeddings, rays, img_idx, sched_mult, N_samples=64, use
                 img_idx=img_idx.contiguous().long(), perturb_rand=as_f32(perturb_rand), u0=as_f32(u0),
                 u1=as_f32(u1), dtype=_dtype_code(kwargs.get("precision") or default_precision()),
                 n_images=0, no_grad=False, grad_sink=kwargs.get("grad_sink"),
-                depths=kwargs.get("return_depths"), after_fine_bwd=kwargs.get("after_fine_bwd"))
+                depths=kwargs.get("return_depths"), after_fine_bwd=kwargs.get("after_fine_bwd"),
+                workspace_cache=kwargs.get("workspace_cache"), reuse_packed=bool(kwargs.get("reuse_packed")))
     emb = lambda k: embeddings[k].weight if k in embeddings else None
     ea_c = emb("coarse_a") if coarse.encode_appearance else None
     ec_c = emb("coarse_c") if coarse.encode_candidate else None
