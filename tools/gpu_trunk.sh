@@ -3,7 +3,7 @@
 cd $GRAFT_REPO_ROOT
 T=${1:-trunk}
 mkdir -p gpurun_out
-timeout -s KILL 600 python -m pytest tests/test_gemm_gpu.py -m gpu -q --timeout 300 -x -k "trunk" 2>&1 | tail -15 | cut -c1-300 > gpurun_out/${T}_pytest.log
+timeout -s KILL 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q --timeout 120 -x -k "trunk" 2>&1 | tail -15 | cut -c1-300 > gpurun_out/${T}_pytest.log
 tail -5 gpurun_out/${T}_pytest.log
 timeout -s KILL 200 python tools/bench_gemm.py trunk > gpurun_out/${T}_gemm.txt 2>&1
 cat gpurun_out/${T}_gemm.txt | tail -5
