@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 T=${1:-r2e}
 timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 600 2>&1 | grep -E "^(E  |FAILED|ERROR|[0-9]+ (passed|failed)|worst)" | cut -c1-300 | head -60 > gpurun_out/${T}_pytest.log
 tail -5 gpurun_out/${T}_pytest.log
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout -s KILL 600 python bench.py --steps 100 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 cut -c1-300 gpurun_out/${T}_bench.json
 timeout -s KILL 600 python bench.py --workload render --steps 3 --warmup 1 > gpurun_out/${T}_render.json 2> gpurun_out/${T}_render.err
