@@ -324,19 +324,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
           named_bar_sync(bar_id, 128);
         }
+        // accumulator columns per TMEM load: 32, or 16 in the variant that carries both a per-ray bias and row-dot
+        // heads (its epilogue spilled registers inside this loop at the 96 the 18-warp block allows: 5 warps per
+        // scheduler x 32 x 96 is all of a scheduler's register file)
+        constexpr int kLd = (kRB && kHD) ? 16 : 32;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t acc_r[32];
-          tmem_ld_32x32(taddr + ch * 64 + half * 32, acc_r);
+        for (int part = 0; part < 64 / kLd; ++part) {
+          uint32_t acc_r[kLd];
+          if constexpr (kLd == 32) tmem_ld_32x32(taddr + ch * 64 + part * 32, acc_r);
+          else tmem_ld_32x16(taddr + ch * 64 + part * 16, acc_r);
           tmem_ld_wait();
-          if (half == 1 && ch == last) {
+          if (part == 64 / kLd - 1 && ch == last) {
             // accumulator fully read by this thread: hand it back to the MMA warp
             tc_fence_before_sync();
             mbar_arrive(&bar_tempty[acc]);
           }
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int c8 = half * 4 + c4;
+          for (int c4 = 0; c4 < kLd / 8; ++c4) {
+            const int c8 = part * (kLd / 8) + c4;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc_r[c4 * 8 + e]);
