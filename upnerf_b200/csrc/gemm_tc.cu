@@ -150,6 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int h = 0; h < args.ep.n_heads; ++h)
         sVec[(2 + h) * kMaxN + i] = args.ep.head_w[h * N + i];
     }
+    // two-contributor head exchange (below): [3 buffers][row][3 sums + arrival count], zero between uses
+    for (int i = t; i < 3 * kBM * 4; i += kEpiThreads) sHead[i] = 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -468,7 +470,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // exchange buffer: a slot is rewritten two uses of the same group set later, i.e. after a barrier the
         // combiner of the earlier tile has passed too (sets alternate tile by tile when nchunks == 2)
         const int hb = nchunks == 2 ? ((t >> 1) & 1) : (t & 1);
-        if (mine) {
+        const bool mine2 = first >= c0 && first < nchunks;   // my box carries head columns
+        if (ncontrib == 2) {
+          // Exactly two groups hold a partial sum per row (the stacked candidate|rgb layer: boxes 2 and 3; 128-wide
+          // layers: both boxes).  No barrier: each adds its partial into the row's slot with shared-memory atomics
+          // and counts its arrival; whoever arrives second finalises the row and clears the slot.  a + b is
+          // commutative, so the result does not depend on who is first.  Three buffers: a group cannot be three
+          // tiles ahead of another (it would need the accumulator the other one has not yet handed back).
+          if (mine2) {
+            float* acc3 = sHead + ((t % 3) * kBM + row_in_tile) * 4;
+#pragma unroll
+            for (int h = 0; h < kMaxHeads; ++h)
+              if (h < nh) atomicAdd(&acc3[h], hacc[h].x + hacc[h].y);
+            __threadfence_block();
+            const int prev = atomicAdd(reinterpret_cast<int*>(&acc3[3]), 1);
+            if (prev == 1) {
+              __threadfence_block();
+              volatile float* va = acc3;
+              for (int h = 0; h < nh; ++h) {
+                float x = ep.head_b[h] + va[h];
+                va[h] = 0.f;
+                if (ep.head_act == 1) x = softplus_ref(x);
+                else if (ep.head_act == 2) x = sigmoid_ref(x);
+                if (row_ok) ep.head_out[grow * nh + h] = x;
+              }
+              *reinterpret_cast<volatile int*>(&acc3[3]) = 0;
+            }
+          }
+        } else if (mine) {
           float* slot = sHead + ((hb * kGroups + grp) * kBM + row_in_tile) * kMaxHeads;
 #pragma unroll
           for (int h = 0; h < kMaxHeads; ++h)
